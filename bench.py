@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- MCMC chain-steps/s (and ESS/s) of the fused Metropolis kernel on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+    torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, NCCL)
+
+A "step" is ONE launch of the fused kernel advancing every chain of the batch by `--mcmc-steps`
+Metropolis steps (proposal -> forward solve -> Phi -> accept/reject -> moments).  Workloads
+(BASELINE.json `configs`):
+    burgers_pcn_256   configs[2]: Burgers pCN beta=0.25, 1024 chains x 256 cells per GPU   (default)
+    burgers_pcn_1024  configs[3]: Burgers pCN, 8192 chains x 1024 cells per GPU (65536 over 8 GPUs)
+    lorenz_rw         configs[1]: Lorenz-96 K=6 J=4 T=20, RW delta=0.125, 4096 chains per GPU
+Scaling is weak: the per-GPU batch is fixed, chains are sharded by global chain id, no data-path
+collective; one all-reduce of pooled moments/counters at the end (inside the timed region).
+
+`--impl reference` times the CPU restatement of the reference's sampler (oracle/, NumPy; the
+reference itself is pure Python + NumPy and cannot travel to the GPU box) on all host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TRUTH = np.array([0.025, -0.025, -0.02])
+PRIOR_MEAN = np.array([1.5, 0.25, -0.5])
+
+WORKLOADS = {
+    "burgers_pcn_256": dict(model="burgers", N=256, chains=1024, mcmc_steps=50, beta=0.25),
+    "burgers_pcn_1024": dict(model="burgers", N=1024, chains=8192, mcmc_steps=4, beta=0.25),
+    "lorenz_rw": dict(model="lorenz", chains=4096, mcmc_steps=2, delta=0.125, T=20.0),
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side (oracle port): used by the cpu_baseline leg and by --impl reference
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """Advance ONE chain by n_steps with the NumPy restatement of the reference sampler."""
+    wl, seed, n_steps, u_start = args
+    from oracle import burgers_np as B, mcmc_np as O, lorenz_np as L
+    rng = np.random.default_rng(seed)
+    if wl["model"] == "burgers":
+        P = B.BurgersProblem(wl["N"])
+        y = P.G_params(TRUTH)
+        pot = O.Potential(P, y, 0.05 ** 2 * np.identity(5))
+        z = 0.25 * rng.standard_normal((n_steps, 3))
+        t0 = time.perf_counter()
+        # the reference evaluates Phi(u) and Phi(v) every step (accepter.py:121-122)
+        r = O.run_chain(pot, u_start, z, rng.random(n_steps), O.PCN, O.PCN, wl["beta"], recompute_phi_u=True)
+        return time.perf_counter() - t0, n_steps, r["accepts"], P.total_n_fv
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lorenz_problem_K6_J4.npz"))
+    op = L.LorenzProblem(6, 4, wl["T"], 1, g["prior_means"], g["IC"])
+    pot = O.Potential(op, g["y"], 0.25 * np.diag(g["var"]))
+    z = rng.standard_normal((n_steps, 3)) * np.sqrt([10., 1, 10])
+    t0 = time.perf_counter()
+    r = O.run_chain(pot, g["u0"], z, rng.random(n_steps), O.RW, O.RW, wl["delta"],
+                    prior_cov=np.diag([10., 1, 10]), recompute_phi_u=True)
+    return time.perf_counter() - t0, n_steps, r["accepts"], op.n_accepted + op.n_rejected
+
+
+def cpu_sample(wl, n_steps, n_workers, u_start):
+    """n_workers independent chains x n_steps on n_workers processes. Returns chain-steps/s."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(n_workers) as pool:
+        res = pool.map(_cpu_worker, [(wl, 1000 + i, n_steps, u_start) for i in range(n_workers)])
+    wall = time.perf_counter() - t0
+    busy = max(r[0] for r in res)
+    steps = sum(r[1] for r in res)
+    return steps / busy, busy, wall, res
+
+
+def cpu_steps_for(wl):
+    return {"burgers": 150 if wl.get("N", 0) <= 256 else 6, "lorenz": 2}[wl["model"]]
+
+
+def posterior_start(wl):
+    """A state near the posterior, so the CPU sample does the same kind of work as the warmed-up
+    GPU chains (solves from the prior mean cost 2.4x more FV steps)."""
+    if wl["model"] == "burgers":
+        return TRUTH - PRIOR_MEAN
+    return None
+
+
+def run_reference(args, wl, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = cpu_steps_for(wl)
+    u_start = posterior_start(wl)
+    for _ in range(args.warmup if args.warmup < 2 else 1):      # process start-up / import warm-up
+        cpu_sample(wl, 1, cores, u_start)
+    t_busy = 0.0
+    steps = 0
+    for _ in range(args.steps):
+        v, busy, wall, res = cpu_sample(wl, n, cores, u_start)
+        t_busy += busy
+        steps += sum(r[1] for r in res)
+    value = steps / t_busy
+    sample = "%d processes x %d chain-steps per bench step (NumPy restatement, 2 forward solves per step as in the reference)" % (cores, n)
+    line = dict(impl="reference", metric="chain_steps_per_sec", value=value, unit="chain-steps/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * t_busy / max(args.steps, 1),
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=workload_config(wl, name, args),
+                cpu_baseline=dict(value=value, unit="chain-steps/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit="chain-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(wl, name, args):
+    cfg = dict(workload=name, chains_per_gpu=wl["chains"], mcmc_steps_per_launch=wl["mcmc_steps"])
+    if wl["model"] == "burgers":
+        cfg.update(cells=wl["N"], proposer="pCN", beta=wl["beta"], T=1.0, prior="N(u_p, 0.25^2 I_3)",
+                   noise_std=0.05, numerics=args.numerics)
+    else:
+        cfg.update(K=6, J=4, T=wl["T"], proposer="RW", delta=wl["delta"], solves_per_step=2,
+                   rtol=1e-3, atol=1e-6)
+    cfg["untimed_burn_in_steps"] = args.burn_in if wl["model"] == "burgers" else 0
+    cfg["l2"] = "flushed between timed launches (256 MiB memset, untimed); working set << L2 anyway"
+    cfg["parallelism"] = "chains sharded by global id, dp%d" % args.gpus
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (NVML) during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+    NOTE = {"sw_power_cap": 0x4}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons = [], set()
+        self.sm_max = None
+        self.stop_flag = False
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        if not self.samples:
+            return None
+        return dict(sm_mhz=float(np.median(self.samples)), sm_max_mhz=float(self.sm_max), reasons=sorted(self.reasons),
+                    samples=len(self.samples))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+def build_problem(M, wl, numerics):
+    if wl["model"] == "burgers":
+        f = M.BurgersFVM(N=wl["N"], numerics=numerics)
+        y = f.at_parameters(TRUTH)           # noise-free synthetic observations G(u*) (burgers_mcmc.py:116)
+        prior = M.GaussianDistribution(PRIOR_MEAN, 0.25 ** 2 * np.identity(3))
+        pot = M.EvolutionPotential(f, y, M.GaussianDistribution(np.zeros(5), 0.05 ** 2 * np.identity(5)))
+        proposer = M.ConstSteppCNProposer(wl["beta"], prior)
+        accepter = M.CountedAccepter(M.pCNAccepter(pot))
+        u0 = np.zeros(3)
+        return pot, proposer, accepter, u0
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lorenz_problem_K6_J4.npz"))
+    f = M.Lorenz96Moments(6, 4, wl["T"], 1.0, g["prior_means"], g["IC"])
+    prior = M.GaussianDistribution(np.zeros(3), np.diag([10., 1, 10]))
+    pot = M.EvolutionPotential(f, g["y"], M.GaussianDistribution(np.zeros(30), 0.25 * np.diag(g["var"])))
+    proposer = M.ConstStepStandardRWProposer(wl["delta"], prior)
+    accepter = M.CountedAccepter(M.StandardRWAccepter(pot, prior))
+    return pot, proposer, accepter, g["u0"]
+
+
+def algorithmic_flops(wl, work_a, work_b):
+    """Burgers 29 FLOP per cell per SSPRK2 time step; Lorenz 3444 FLOP per
+    Dormand-Prince attempt + 48 per accepted step (K=6, J=4)."""
+    if wl["model"] == "burgers":
+        return 29.0 * wl["N"] * work_a
+    return 3444.0 * (work_a + work_b) + 48.0 * work_a
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="burgers_pcn_256", choices=sorted(WORKLOADS))
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
+    ap.add_argument("--mcmc-steps", type=int, default=0, help="Metropolis steps per launch")
+    ap.add_argument("--numerics", default="fused", choices=["exact", "fused"])
+    ap.add_argument("--burn-in", type=int, default=1500, help="untimed Metropolis steps before warm-up (Burgers)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workload lines")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.chains:
+        wl["chains"] = args.chains
+    if args.mcmc_steps:
+        wl["mcmc_steps"] = args.mcmc_steps
+    if args.impl == "reference":
+        return run_reference(args, wl, args.workload)
+
+    import torch
+    import torch.distributed as dist
+    import ip_mcmc_b200 as M
+    from ip_mcmc_b200 import parallel
+    from ip_mcmc_b200.engine import ChainBatch, F64
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def measure(wl, K, W, with_e2e=True, trace_chains=64, burn_in=0, start=None):
+        B, S = wl["chains"], wl["mcmc_steps"]
+        pot, proposer, accepter, u0 = build_problem(M, wl, args.numerics)
+        sampler = M.MCMCSampler(proposer, accepter, np.random.default_rng(2))
+        spec, pot, a = sampler._compile(10 ** 9, 0, 1, None)
+        problem = pot.problem()
+        if start is not None:
+            u0 = start
+        chains = ChainBatch(problem, u0, n_chains=B, chain_offset=rank * B)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        trace = torch.empty((B, S, 3), dtype=F64, device=dev)
+        kept = []
+        if burn_in:                                         # untimed burn-in: leave the prior-mean start
+            chains.run(spec, burn_in)
+        for _ in range(W):
+            chains.run(spec, S, trace=trace)
+        torch.cuda.synchronize()
+        c0 = chains.counters.sum(0).cpu().numpy()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler_clk = ClockSampler(local)
+        sampler_clk.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K + 1)]
+        launches0 = chains.launches
+        t_wall0 = time.perf_counter()
+        for k in range(K):
+            flush.zero_()                                   # evict L2 between timed launches (untimed)
+            ev[k][0].record()
+            chains.run(spec, S, trace=trace)
+            ev[k][1].record()
+            kept.append(trace[:trace_chains].clone())
+        ev[K][0].record()
+        pooled = parallel.allreduce_pooled(chains.pooled(), 3)  # the only collective of the job
+        ev[K][1].record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+        sampler_clk.stop_flag = True
+        sampler_clk.join()
+        kern_ms = [a.elapsed_time(b) for a, b in ev[:K]]
+        red_ms = ev[K][0].elapsed_time(ev[K][1])
+        total_ms = parallel.max_over_ranks(sum(kern_ms) + red_ms, dev)
+        c1 = chains.counters.sum(0).cpu().numpy()
+        dc = (c1 - c0).astype(np.float64)
+        cnt = torch.tensor(dc, dtype=F64, device=dev)
+        if world > 1:
+            dist.all_reduce(cnt)
+        dc_all = cnt.cpu().numpy()
+        steps_all = B * S * K * world
+        value = steps_all / (total_ms * 1e-3)
+        # roofline of the dominant (only) kernel, this rank
+        flops = algorithmic_flops(wl, dc[2], dc[3])
+        achieved = flops / (sum(kern_ms) * 1e-3) / 1e12
+        hbm_bytes = B * (2 * 8 * 4 + 8 * 3 * S) * K        # u, Phi in/out + the recorded trace
+        tr = torch.stack(kept, dim=1).reshape(min(trace_chains, B), K * S, 3).cpu().numpy()
+        ess_tot, ess_per = M.stats.ess_multichain(tr)
+        ess_per_chain = ess_tot / tr.shape[0]
+        out = dict(value=value, total_ms=total_ms, kern_ms=kern_ms, red_ms=red_ms, achieved=achieved,
+                   hbm_gbs=hbm_bytes / (sum(kern_ms) * 1e-3) / 1e9, counters=dc_all, steps_all=steps_all,
+                   acceptance=dc_all[1] / max(dc_all[0], 1), ess_per_sec=ess_per_chain * B * world / (total_ms * 1e-3),
+                   ess_per_chain=ess_per_chain, clocks=sampler_clk.summary(), launches=chains.launches - launches0,
+                   pooled=pooled.cpu().numpy(), wall_s=t_wall, mean_work_per_solve=dc_all[2] / max(dc_all[3], 1)
+                   if wl["model"] == "burgers" else (dc_all[2] + dc_all[3]) / max(2 * dc_all[0], 1))
+        if with_e2e:
+            # end to end through the public API with HOST buffers: numpy u_0 in, numpy samples out
+            u_host = chains.u.cpu().numpy()
+            ms_host = chains.model_state.cpu().numpy() if chains.model_state is not None else None
+            if ms_host is not None:
+                pot.G.IC = ms_host[0]
+            sampler.run(u_host, S, 0, 1, n_chains=B, chain_offset=rank * B)   # warm
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(K):
+                samples = sampler.run(u_host, S, 0, 1, n_chains=B, chain_offset=rank * B)
+            torch.cuda.synchronize()
+            dt = parallel.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
+            out["e2e"] = dict(value=B * S * K * world / (dt * 1e-3), unit="chain-steps/s",
+                              h2d_bytes_per_step=int(sampler.last_run["h2d_bytes"]),
+                              d2h_bytes_per_step=int(sampler.last_run["d2h_bytes"]))
+        return out
+
+    peak = M.fp64_peak_tflops(5)
+    res = measure(wl, args.steps, max(args.warmup, 3), burn_in=args.burn_in if wl['model'] == 'burgers' else 0)
+    extra = {}
+    if not args.no_extra and world == 1 and args.workload == "burgers_pcn_256":
+        for name in ("lorenz_rw", "burgers_pcn_1024"):
+            r = measure(dict(WORKLOADS[name]), 3, 3, with_e2e=False, trace_chains=8,
+                        start=(TRUTH - PRIOR_MEAN) if name.startswith('burgers') else None)
+            extra[name] = dict(chain_steps_per_sec=r["value"], acceptance=r["acceptance"],
+                               roofline_tflops=r["achieved"], roofline_frac=r["achieved"] / peak,
+                               ms_per_step=r["total_ms"] / 3, config=workload_config(WORKLOADS[name], name, args))
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = dict(bound="fp64", achieved=res["achieved"], peak=peak, unit="TFLOP/s", frac=res["achieved"] / peak,
+                    traffic=None,
+                    peak_source="DFMA micro-benchmark (ipmcmc_fp64_peak) measured in this run; MEASURED_PEAKS.json has "
+                                "no fp64 entry (nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
+                    flops_model="29 FLOP per cell per SSPRK2 step x device-counted FV steps" if wl["model"] == "burgers"
+                    else "3444 FLOP per RK45 attempt x device-counted attempts",
+                    hbm=dict(achieved=res["hbm_gbs"], peak=hbm_peak, unit="GB/s", frac=res["hbm_gbs"] / hbm_peak,
+                             peak_source="MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"))
+    line = dict(metric="chain_steps_per_sec", value=res["value"], unit="chain-steps/s", n_gpus=world, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=res["total_ms"] / args.steps, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=workload_config(wl, args.workload, args), roofline=roofline, e2e=res.get("e2e"),
+                gpu_launches=int(res["launches"]), clocks=res["clocks"], ess_per_sec=res["ess_per_sec"],
+                ess_per_chain_in_timed_window=res["ess_per_chain"], acceptance_rate=res["acceptance"],
+                mean_work_per_solve=res["mean_work_per_solve"], allreduce_ms=res["red_ms"],
+                posterior_mean=[float(x) for x in res["pooled"][1:4]], extra_workloads=extra)
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        n = cpu_steps_for(wl)
+        v, busy, wall, _ = cpu_sample(wl, n, cores, posterior_start(wl))
+        line["cpu_baseline"] = dict(value=v, unit="chain-steps/s", cores=cores, kind="port",
+                                    sample="%d processes x %d chain-steps of the same workload, NumPy restatement of "
+                                           "the reference sampler (2 forward solves per step), %.1f s" % (cores, n, busy))
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

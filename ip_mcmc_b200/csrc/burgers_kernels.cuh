@@ -1,0 +1,174 @@
+// Burgers kernels: batched forward evaluation and the fused Metropolis kernel.
+// One chain per warp, one warp per CTA (the hardware block scheduler then balances the
+// data-dependent solve lengths across the 148 SMs); the FV state never leaves registers, the end
+// state is staged once per solve in shared memory for the windowed trapezoid measurement.
+#pragma once
+#include "burgers.cuh"
+#include "sampler.cuh"
+
+namespace ipmcmc {
+
+// shared memory layout per warp: state[N] | G[MAX_OBS] | r2[MAX_OBS]
+__host__ __device__ inline size_t burgers_smem_bytes(int N) { return (size_t)(N + 2 * IPMCMC_MAX_OBS) * sizeof(double); }
+
+// Measurer.__call__ (utilities.py:100-109): m_i = 10 * trapz(values[l:r], dx) with numpy's
+// evaluation (dx*(y[1:]+y[:-1])/2.0).sum() in pairwise order; lane i handles window i.
+__device__ __forceinline__ void burgers_measure(const BurgersDev &B, const double *state, double *Gs, int lane) {
+    for (int i = lane; i < B.pot.q; i += 32) {
+        const int l = B.win_left[i], r = B.win_right[i];
+        const int nterm = r - l - 1;
+        double sum = 0.0;
+        if (nterm >= 1) {
+            const double dxm = B.dx_meas;
+            sum = np_pairwise_sum([&](int j) { return dxm * (state[j + 1] + state[j]) / 2.0; }, l, nterm);
+        }
+        Gs[i] = 10.0 * sum;
+    }
+    __syncwarp();
+}
+
+// G(u) and Phi(u) for the parameter vector whose component i sits on lane i (value `ui`).
+// Leaves the end state in smem `state` and G in `Gs`.  Returns Phi; n_fv by reference.
+template <int CPL, int NUMERICS>
+__device__ __noinline__ double burgers_phi(const BurgersDev &B, double ui, double *state, double *Gs, double *r2,
+                                              int lane, int &n_fv) {
+    // FVMObservationOperator.__call__ (utilities.py:40-41): IC(u_0 + u)
+    const double pi = (lane < B.d) ? B.param_mean[lane] + ui : 0.0;
+    const double p0 = shfl(pi, 0), p1 = shfl(pi, 1), p2 = shfl(pi, 2);
+    BurgersWarp<CPL, NUMERICS> W;
+    n_fv = W.integrate(B, p0, p1, p2, lane);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+        const int c = lane * CPL + k;
+        if (c < B.N) state[c] = W.u[k];
+    }
+    __syncwarp();
+    burgers_measure(B, state, Gs, lane);
+    return potential_from_G(B.pot, Gs, r2, lane, 32, FULL);
+}
+
+template <int CPL, int NUMERICS>
+__global__ void __launch_bounds__(32) burgers_forward_kernel(const __grid_constant__ BurgersDev B, long long n,
+                                                             const double *__restrict__ u, double *__restrict__ G,
+                                                             double *__restrict__ phi, double *__restrict__ state_out,
+                                                             long long *__restrict__ work) {
+    extern __shared__ double smem[];
+    double *state = smem, *Gs = smem + B.N, *r2 = Gs + IPMCMC_MAX_OBS;
+    const int lane = lane_id();
+    for (long long c = blockIdx.x; c < n; c += gridDim.x) {
+        const double ui = (lane < B.d) ? u[c * B.d + lane] : 0.0;
+        int n_fv;
+        const double ph = burgers_phi<CPL, NUMERICS>(B, ui, state, Gs, r2, lane, n_fv);
+        if (G)
+            for (int i = lane; i < B.pot.q; i += 32) G[c * B.pot.q + i] = Gs[i];
+        if (state_out)
+            for (int i = lane; i < B.N; i += 32) state_out[c * B.N + i] = state[i];
+        if (lane == 0) {
+            if (phi) phi[c] = ph;
+            if (work) {
+                work[2 * c] = n_fv;
+                work[2 * c + 1] = 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int CPL, int NUMERICS>
+__global__ void __launch_bounds__(32) burgers_chain_kernel(const __grid_constant__ BurgersDev B,
+                                                           const __grid_constant__ SamplerDev S,
+                                                           const __grid_constant__ ChainBufDev C, long long n_chains,
+                                                           long long n_steps) {
+    extern __shared__ double smem[];
+    double *state = smem, *Gs = smem + B.N, *r2 = Gs + IPMCMC_MAX_OBS;
+    const int lane = lane_id();
+    const Group Gp{0, 32, lane, FULL};
+    const int d = S.d;
+    for (long long c = blockIdx.x; c < n_chains; c += gridDim.x) {
+        const long long cg = S.chain_offset + c;
+        double ui = (lane < d) ? C.u[c * d + lane] : 0.0;
+        double phi_u = C.phi[c];
+        long long cnt[CNT_N];
+#pragma unroll
+        for (int k = 0; k < CNT_N; ++k) cnt[k] = 0;
+        int n_fv;
+        if (isnan(phi_u)) {  // first launch: Phi(u_0) not known yet
+            phi_u = burgers_phi<CPL, NUMERICS>(B, ui, state, Gs, r2, lane, n_fv);
+            cnt[CNT_WORK_A] += n_fv;
+            cnt[CNT_WORK_B] += 1;
+        }
+        double reg_u = (S.accepter == IPMCMC_ACCEPT_RW) ? prior_regulariser(S, Gp, ui) : 0.0;
+        Welford mom{C.mom_count[c], (lane < d) ? C.mom_mean[c * d + lane] : 0.0,
+                    (lane < d) ? C.mom_m2[c * d + lane] : 0.0};
+        long long n_rec = 0;
+
+        for (long long s = 0; s < n_steps; ++s) {
+            const long long gstep = S.first_step + s;
+            double ca, cb;
+            step_coefs(S, gstep, ca, cb);
+            const double w = proposal_noise(S, C, Gp, c, cg, s, n_steps, gstep);
+            const double vi = ca * ui + cb * w;
+            if (C.vlog && lane < d) C.vlog[(c * n_steps + s) * d + lane] = vi;
+            bool accepted = false;
+            double phi_v = nan(""), a = nan("");
+            n_fv = 0;
+            const bool ok = !S.has_constraint || constraint_ok(S, Gp, vi);
+            if (ok) {
+                if (S.recompute_phi_u) {  // the reference's 2 solves per step (accepter.py:121-122)
+                    int nf0;
+                    phi_u = burgers_phi<CPL, NUMERICS>(B, ui, state, Gs, r2, lane, nf0);
+                    cnt[CNT_WORK_A] += nf0;
+                    cnt[CNT_WORK_B] += 1;
+                }
+                phi_v = burgers_phi<CPL, NUMERICS>(B, vi, state, Gs, r2, lane, n_fv);
+                cnt[CNT_WORK_A] += n_fv;
+                cnt[CNT_WORK_B] += 1;
+                double reg_v = 0.0;
+                if (S.accepter == IPMCMC_ACCEPT_RW) reg_v = prior_regulariser(S, Gp, vi);
+                a = exp((phi_u + reg_u) - (phi_v + reg_v));
+                const double U = C.inject_u ? C.inject_u[c * n_steps + s]
+                                            : draw_uniform(S.seed, (uint64_t)cg, (uint64_t)gstep);
+                accepted = a > U;  // strict, un-clipped; NaN compares false (accepter.py:61-62)
+                if (!isfinite(phi_v)) cnt[CNT_NONFINITE] += 1;
+                if (accepted) {
+                    ui = vi;
+                    phi_u = phi_v;
+                    reg_u = reg_v;
+                }
+            } else {
+                cnt[CNT_CONSTRAINT] += 1;
+            }
+            cnt[CNT_CALLS] += 1;
+            cnt[CNT_ACCEPTS] += accepted ? 1 : 0;
+            if (C.steplog && lane == 0) {
+                double *L = C.steplog + (c * n_steps + s) * 4;
+                L[0] = phi_v;
+                L[1] = a;
+                L[2] = accepted ? 1.0 : 0.0;
+                L[3] = (double)n_fv;
+            }
+            // recording (sampler.py:23-28)
+            if (S.record_interval > 0 && gstep >= S.record_start &&
+                ((gstep - S.record_start + 1) % S.record_interval) == 0) {
+                mom.add(ui);
+                if (C.trace && n_rec < C.n_record && lane < d) C.trace[(c * C.n_record + n_rec) * d + lane] = ui;
+                ++n_rec;
+            }
+        }
+        // write back
+        if (lane < d) {
+            C.u[c * d + lane] = ui;
+            C.mom_mean[c * d + lane] = mom.mean;
+            C.mom_m2[c * d + lane] = mom.m2;
+        }
+        if (lane == 0) {
+            C.phi[c] = phi_u;
+            C.mom_count[c] = mom.count;
+#pragma unroll
+            for (int k = 0; k < CNT_N; ++k) C.counters[c * CNT_N + k] += cnt[k];
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace ipmcmc

@@ -1,0 +1,518 @@
+// libipmcmc.so -- C ABI (include/ipmcmc.h) over the sm_100a kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "burgers_kernels.cuh"
+#include "lorenz_kernels.cuh"
+
+using namespace ipmcmc;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) return fail(IPMCMC_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e));  \
+    } while (0)
+
+extern "C" const char *ipmcmc_last_error(void) { return g_err.c_str(); }
+extern "C" int ipmcmc_abi_version(void) { return IPMCMC_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------------
+// problem handle
+// ------------------------------------------------------------------------------------------------
+struct ipmcmc_problem {
+    int model = 0;
+    int numerics = 0;
+    BurgersDev b;
+    LorenzDev l;
+    std::vector<void *> owned;   // device allocations freed in destroy
+    double *scratch = nullptr;   // device [2*MAX_DIM*MAX_DIM]: proposal factor | prior Cholesky
+};
+
+static int upload(ipmcmc_problem *p, const void *host, size_t bytes, void **dev) {
+    CUDA_TRY(cudaMalloc(dev, bytes ? bytes : 8));
+    p->owned.push_back(*dev);
+    if (bytes) CUDA_TRY(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int fill_potential(ipmcmc_problem *p, const ipmcmc_potential_desc &d, PotentialDev &out) {
+    if (d.n_obs < 1 || d.n_obs > IPMCMC_MAX_OBS) return fail(IPMCMC_EINVAL, "n_obs=%d outside [1,%d]", d.n_obs, IPMCMC_MAX_OBS);
+    if (!d.y) return fail(IPMCMC_EINVAL, "potential.y is NULL");
+    memset(&out, 0, sizeof out);
+    out.q = d.n_obs;
+    out.dense = d.whiten_dense ? 1 : 0;
+    out.log_const = d.log_const;
+    for (int i = 0; i < d.n_obs; ++i) out.y[i] = d.y[i];
+    if (!out.dense) {
+        if (!d.perm || !d.scale) return fail(IPMCMC_EINVAL, "potential.perm/scale is NULL");
+        for (int i = 0; i < d.n_obs; ++i) {
+            if (d.perm[i] < 0 || d.perm[i] >= d.n_obs) return fail(IPMCMC_EINVAL, "potential.perm[%d] out of range", i);
+            out.perm[i] = d.perm[i];
+            out.scale[i] = d.scale[i];
+        }
+    } else {
+        if (!d.LP) return fail(IPMCMC_EINVAL, "potential.LP is NULL");
+        void *dev;
+        int rc = upload(p, d.LP, sizeof(double) * d.n_obs * d.n_obs, &dev);
+        if (rc) return rc;
+        out.LP = (const double *)dev;
+    }
+    return 0;
+}
+
+static int finish_create(ipmcmc_problem *p, ipmcmc_problem **out) {
+    void *dev;
+    int rc = upload(p, nullptr, 0, &dev);
+    if (rc) return rc;
+    CUDA_TRY(cudaMalloc((void **)&p->scratch, sizeof(double) * 2 * IPMCMC_MAX_DIM * IPMCMC_MAX_DIM));
+    p->owned.push_back(p->scratch);
+    *out = p;
+    return 0;
+}
+
+extern "C" void ipmcmc_destroy(ipmcmc_problem *p) {
+    if (!p) return;
+    for (void *d : p->owned) cudaFree(d);
+    delete p;
+}
+
+static const int kCPL[] = {1, 2, 4, 7, 8, 16, 32};
+
+static int pick_cpl(int N) {
+    for (int c : kCPL)
+        if (32 * c >= N) return c;
+    return 0;
+}
+
+extern "C" int ipmcmc_burgers_create(const ipmcmc_burgers_desc *d, ipmcmc_problem **out) {
+    if (!d || !out) return fail(IPMCMC_EINVAL, "NULL argument");
+    if (d->n_cells < 2) return fail(IPMCMC_EINVAL, "n_cells=%d < 2", d->n_cells);
+    if (!pick_cpl(d->n_cells)) return fail(IPMCMC_EUNSUPPORTED, "n_cells=%d > 1024 (register-resident warp solver)", d->n_cells);
+    if (d->n_params != 3) return fail(IPMCMC_EUNSUPPORTED, "PerturbedRiemannIC takes 3 parameters, got %d", d->n_params);
+    if (d->numerics != IPMCMC_NUMERICS_EXACT && d->numerics != IPMCMC_NUMERICS_FUSED) return fail(IPMCMC_EINVAL, "bad numerics");
+    if (!d->x || !d->param_mean || !d->win_left || !d->win_right) return fail(IPMCMC_EINVAL, "NULL table");
+    if (!(d->dx > 0)) return fail(IPMCMC_EINVAL, "dx must be > 0");
+    auto *p = new ipmcmc_problem();
+    p->model = IPMCMC_MODEL_BURGERS;
+    p->numerics = d->numerics;
+    BurgersDev &b = p->b;
+    memset(&b, 0, sizeof b);
+    b.N = d->n_cells;
+    b.d = d->n_params;
+    b.max_fv_steps = d->max_fv_steps > 0 ? d->max_fv_steps : 64 * d->n_cells + 1024;
+    b.T = d->T;
+    b.dx = d->dx;
+    b.half_dx = 0.5 * d->dx;
+    b.neg_inv_dx = -1.0 / d->dx;
+    int ex;
+    b.dx_pow2 = (std::frexp(d->dx, &ex) == 0.5) ? 1 : 0;
+    b.dx_meas = d->dx_meas;
+    for (int i = 0; i < b.d; ++i) b.param_mean[i] = d->param_mean[i];
+    int rc = fill_potential(p, d->potential, b.pot);
+    if (rc) { ipmcmc_destroy(p); return rc; }
+    for (int i = 0; i < b.pot.q; ++i) {
+        const int l = d->win_left[i], r = d->win_right[i];
+        if (l < 0 || r > b.N || l > r) { ipmcmc_destroy(p); return fail(IPMCMC_EINVAL, "window %d = [%d,%d) outside [0,%d]", i, l, r, b.N); }
+        b.win_left[i] = l;
+        b.win_right[i] = r;
+    }
+    void *dev;
+    rc = upload(p, d->x, sizeof(double) * (b.N + 2), &dev);
+    if (rc) { ipmcmc_destroy(p); return rc; }
+    b.x = (const double *)dev;
+    rc = finish_create(p, out);
+    if (rc) ipmcmc_destroy(p);
+    return rc;
+}
+
+extern "C" int ipmcmc_lorenz_create(const ipmcmc_lorenz_desc *d, ipmcmc_problem **out) {
+    if (!d || !out) return fail(IPMCMC_EINVAL, "NULL argument");
+    if (d->K < 3 || d->K > 32) return fail(IPMCMC_EUNSUPPORTED, "K=%d outside [3,32] (one lane per slow variable)", d->K);
+    if (d->J != 1 && d->J != 2 && d->J != 4 && d->J != 8) return fail(IPMCMC_EUNSUPPORTED, "J=%d not in {1,2,4,8}", d->J);
+    if (d->potential.n_obs != 5 * d->K) return fail(IPMCMC_EINVAL, "n_obs=%d, expected 5*K=%d", d->potential.n_obs, 5 * d->K);
+    if (!d->param_mean) return fail(IPMCMC_EINVAL, "NULL param_mean");
+    auto *p = new ipmcmc_problem();
+    p->model = IPMCMC_MODEL_LORENZ;
+    LorenzDev &l = p->l;
+    memset(&l, 0, sizeof l);
+    l.K = d->K;
+    l.J = d->J;
+    l.nvar = d->K * (d->J + 1);
+    l.max_attempts = d->max_attempts > 0 ? d->max_attempts : (1 << 20);
+    l.T = d->T;
+    l.c = d->c;
+    l.rtol = d->rtol;
+    l.atol = d->atol;
+    for (int i = 0; i < 3; ++i) l.param_mean[i] = d->param_mean[i];
+    int rc = fill_potential(p, d->potential, l.pot);
+    if (rc) { ipmcmc_destroy(p); return rc; }
+    rc = finish_create(p, out);
+    if (rc) ipmcmc_destroy(p);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------
+static int grid_for(long long n_blocks) { return (int)(n_blocks < 2147483647LL ? n_blocks : 2147483647LL); }
+
+template <int CPL, int NUM>
+static int burgers_launch_forward(ipmcmc_problem *p, long long n, const double *u, double *G, double *phi,
+                                  double *state, long long *work, cudaStream_t st) {
+    const size_t smem = burgers_smem_bytes(p->b.N);
+    burgers_forward_kernel<CPL, NUM><<<grid_for(n), 32, smem, st>>>(p->b, n, u, G, phi, state, work);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+template <int CPL, int NUM>
+static int burgers_launch_chain(ipmcmc_problem *p, const SamplerDev &S, const ChainBufDev &C, long long n_chains,
+                                long long n_steps, cudaStream_t st) {
+    const size_t smem = burgers_smem_bytes(p->b.N);
+    burgers_chain_kernel<CPL, NUM><<<grid_for(n_chains), 32, smem, st>>>(p->b, S, C, n_chains, n_steps);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+#define BURGERS_DISPATCH(FN, ...)                                                       \
+    do {                                                                                \
+        const int cpl = pick_cpl(p->b.N);                                               \
+        const bool fused = p->numerics == IPMCMC_NUMERICS_FUSED;                        \
+        switch (cpl) {                                                                  \
+            case 1: return fused ? FN<1, NUM_FUSED>(__VA_ARGS__) : FN<1, NUM_EXACT>(__VA_ARGS__);   \
+            case 2: return fused ? FN<2, NUM_FUSED>(__VA_ARGS__) : FN<2, NUM_EXACT>(__VA_ARGS__);   \
+            case 4: return fused ? FN<4, NUM_FUSED>(__VA_ARGS__) : FN<4, NUM_EXACT>(__VA_ARGS__);   \
+            case 7: return fused ? FN<7, NUM_FUSED>(__VA_ARGS__) : FN<7, NUM_EXACT>(__VA_ARGS__);   \
+            case 8: return fused ? FN<8, NUM_FUSED>(__VA_ARGS__) : FN<8, NUM_EXACT>(__VA_ARGS__);   \
+            case 16: return fused ? FN<16, NUM_FUSED>(__VA_ARGS__) : FN<16, NUM_EXACT>(__VA_ARGS__); \
+            case 32: return fused ? FN<32, NUM_FUSED>(__VA_ARGS__) : FN<32, NUM_EXACT>(__VA_ARGS__); \
+        }                                                                               \
+        return fail(IPMCMC_EUNSUPPORTED, "no kernel for n_cells=%d", p->b.N);           \
+    } while (0)
+
+#define LORENZ_DISPATCH(KERNEL, J, ...)                                                 \
+    do {                                                                                \
+        switch (J) {                                                                    \
+            case 1: KERNEL<1> __VA_ARGS__; break;                                       \
+            case 2: KERNEL<2> __VA_ARGS__; break;                                       \
+            case 4: KERNEL<4> __VA_ARGS__; break;                                       \
+            case 8: KERNEL<8> __VA_ARGS__; break;                                       \
+            default: return fail(IPMCMC_EUNSUPPORTED, "J=%d not in {1,2,4,8}", J);      \
+        }                                                                               \
+        CUDA_TRY(cudaGetLastError());                                                   \
+    } while (0)
+
+extern "C" int ipmcmc_forward(ipmcmc_problem *p, int64_t n, const double *u_dev, double *G_dev, double *phi_dev,
+                              double *state_dev, int64_t *work_dev, void *stream) {
+    if (!p || !u_dev) return fail(IPMCMC_EINVAL, "NULL argument");
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->model == IPMCMC_MODEL_BURGERS) {
+        BURGERS_DISPATCH(burgers_launch_forward, p, n, u_dev, G_dev, phi_dev, state_dev, (long long *)work_dev, st);
+    }
+    if (!state_dev) return fail(IPMCMC_EINVAL, "Lorenz forward needs state_dev (carried initial condition)");
+    const int groups = lorenz_groups(p->l.K);
+    const long long blocks = (n + groups - 1) / groups;
+    LORENZ_DISPATCH(lorenz_forward_kernel, p->l.J,
+                    <<<grid_for(blocks), 32, lorenz_smem_bytes(p->l.K), st>>>(p->l, n, u_dev, G_dev, phi_dev, state_dev,
+                                                                              (long long *)work_dev));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampler
+// ------------------------------------------------------------------------------------------------
+static int make_sampler(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, SamplerDev &S, cudaStream_t st) {
+    const int d = s->dim;
+    if (d < 1 || d > IPMCMC_MAX_DIM) return fail(IPMCMC_EINVAL, "dim=%d outside [1,%d]", d, IPMCMC_MAX_DIM);
+    if (p->model == IPMCMC_MODEL_BURGERS && d != p->b.d) return fail(IPMCMC_EINVAL, "dim=%d but the forward model takes %d parameters", d, p->b.d);
+    if (p->model == IPMCMC_MODEL_LORENZ && d != 3) return fail(IPMCMC_EINVAL, "dim=%d but the Lorenz operator takes (F,h,b)", d);
+    if (s->proposer != IPMCMC_PROPOSE_RW && s->proposer != IPMCMC_PROPOSE_PCN) return fail(IPMCMC_EINVAL, "bad proposer");
+    if (s->accepter != IPMCMC_ACCEPT_RW && s->accepter != IPMCMC_ACCEPT_PCN) return fail(IPMCMC_EINVAL, "bad accepter");
+    if (s->factor_kind < 0 || s->factor_kind > 2) return fail(IPMCMC_EINVAL, "bad factor_kind");
+    if (s->factor_kind && !s->factor) return fail(IPMCMC_EINVAL, "factor is NULL");
+    if (s->accepter == IPMCMC_ACCEPT_RW && !s->prior_chol) return fail(IPMCMC_EINVAL, "ACCEPT_RW needs prior_chol");
+    if (s->coef_sched_dev && s->n_sched < 1) return fail(IPMCMC_EINVAL, "empty schedule");
+    memset(&S, 0, sizeof S);
+    S.d = d;
+    S.proposer = s->proposer;
+    S.accepter = s->accepter;
+    S.factor_kind = s->factor_kind;
+    S.recompute_phi_u = s->recompute_phi_u;
+    S.has_constraint = s->has_constraint;
+    S.coef_u = s->coef_u;
+    S.coef_w = s->coef_w;
+    S.coef_sched = s->coef_sched_dev;
+    S.n_sched = s->n_sched;
+    double *fac = p->scratch, *chol = p->scratch + IPMCMC_MAX_DIM * IPMCMC_MAX_DIM;
+    if (s->factor_kind) {
+        const size_t nb = sizeof(double) * (s->factor_kind == 1 ? d : d * d);
+        CUDA_TRY(cudaMemcpyAsync(fac, s->factor, nb, cudaMemcpyHostToDevice, st));
+        S.factor = fac;
+    }
+    if (s->accepter == IPMCMC_ACCEPT_RW) {
+        CUDA_TRY(cudaMemcpyAsync(chol, s->prior_chol, sizeof(double) * d * d, cudaMemcpyHostToDevice, st));
+        S.prior_chol = chol;
+    }
+    if (s->has_constraint) {
+        if (!s->box_lo || !s->box_hi) return fail(IPMCMC_EINVAL, "constraint box is NULL");
+        for (int i = 0; i < d; ++i) {
+            S.box_lo[i] = s->box_lo[i];
+            S.box_hi[i] = s->box_hi[i];
+            S.box_shift[i] = s->box_shift ? s->box_shift[i] : 0.0;
+        }
+    }
+    S.seed = s->seed;
+    S.chain_offset = s->chain_offset;
+    S.first_step = s->first_step;
+    S.record_start = s->record_start;
+    S.record_interval = s->record_interval;
+    return 0;
+}
+
+extern "C" int ipmcmc_run(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, const ipmcmc_chain_buffers *b,
+                          int64_t n_chains, int64_t n_steps, void *stream) {
+    if (!p || !s || !b) return fail(IPMCMC_EINVAL, "NULL argument");
+    if (n_chains <= 0 || n_steps < 0) return fail(IPMCMC_EINVAL, "n_chains=%lld n_steps=%lld", (long long)n_chains, (long long)n_steps);
+    if (!b->u_dev || !b->phi_dev || !b->mom_count_dev || !b->mom_mean_dev || !b->mom_m2_dev || !b->counters_dev)
+        return fail(IPMCMC_EINVAL, "chain state buffer is NULL");
+    if (p->model == IPMCMC_MODEL_LORENZ && !b->model_state_dev) return fail(IPMCMC_EINVAL, "Lorenz chains need model_state_dev");
+    cudaStream_t st = (cudaStream_t)stream;
+    SamplerDev S;
+    int rc = make_sampler(p, s, S, st);
+    if (rc) return rc;
+    ChainBufDev C;
+    C.u = b->u_dev;
+    C.phi = b->phi_dev;
+    C.model_state = b->model_state_dev;
+    C.mom_count = b->mom_count_dev;
+    C.mom_mean = b->mom_mean_dev;
+    C.mom_m2 = b->mom_m2_dev;
+    C.counters = (long long *)b->counters_dev;
+    C.trace = b->trace_dev;
+    C.n_record = b->n_record;
+    C.steplog = b->steplog_dev;
+    C.vlog = b->vlog_dev;
+    C.inject_w = b->inject_w_dev;
+    C.inject_u = b->inject_u_dev;
+    if (p->model == IPMCMC_MODEL_BURGERS) {
+        BURGERS_DISPATCH(burgers_launch_chain, p, S, C, n_chains, n_steps, st);
+    }
+    const int groups = lorenz_groups(p->l.K);
+    const long long blocks = (n_chains + groups - 1) / groups;
+    LORENZ_DISPATCH(lorenz_chain_kernel, p->l.J,
+                    <<<grid_for(blocks), 32, lorenz_smem_bytes(p->l.K), st>>>(p->l, S, C, n_chains, n_steps));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pooling of per-chain moments: Chan et al. pairwise merge, one CTA, deterministic order
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pool_moments_kernel(long long n_chains, int d, const double *__restrict__ cnt,
+                                                           const double *__restrict__ mean,
+                                                           const double *__restrict__ m2,
+                                                           const long long *__restrict__ counters,
+                                                           double *__restrict__ out) {
+    // thread t < d merges component t over all chains sequentially in chain order (deterministic,
+    // independent of the launch geometry); threads d..d+5 sum the six counters.
+    const int t = threadIdx.x;
+    if (t < d) {
+        double n = 0.0, mu = 0.0, M2 = 0.0;
+        for (long long c = 0; c < n_chains; ++c) {
+            const double nb = cnt[c];
+            if (nb <= 0.0) continue;
+            const double mb = mean[c * d + t], Mb = m2[c * d + t];
+            const double nt = n + nb, delta = mb - mu;
+            mu += delta * (nb / nt);
+            M2 += Mb + delta * delta * (n * nb / nt);
+            n = nt;
+        }
+        out[1 + t] = mu;
+        out[1 + d + t] = M2;
+        if (t == 0) out[0] = n;
+    } else if (t < d + CNT_N) {
+        const int k = t - d;
+        long long s = 0;
+        for (long long c = 0; c < n_chains; ++c) s += counters[c * CNT_N + k];
+        out[1 + 2 * d + k] = (double)s;
+    }
+}
+
+extern "C" int ipmcmc_pool_moments(int64_t n_chains, int32_t dim, const double *mom_count_dev,
+                                   const double *mom_mean_dev, const double *mom_m2_dev, const int64_t *counters_dev,
+                                   double *pooled_dev, void *stream) {
+    if (dim < 1 || dim > IPMCMC_MAX_DIM) return fail(IPMCMC_EINVAL, "dim=%d", dim);
+    if (!mom_count_dev || !mom_mean_dev || !mom_m2_dev || !counters_dev || !pooled_dev) return fail(IPMCMC_EINVAL, "NULL argument");
+    pool_moments_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(n_chains, dim, mom_count_dev, mom_mean_dev, mom_m2_dev,
+                                                             (const long long *)counters_dev, pooled_dev);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer path
+// ------------------------------------------------------------------------------------------------
+__global__ void fill_kernel(double *p, long long n, double v) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+extern "C" int ipmcmc_sample_host(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, int64_t n_chains, int64_t n_steps,
+                                  const double *u0_host, double *model_state_host, double *samples_host,
+                                  int64_t n_record, int64_t *counters_host, double *pooled_host, void *stream) {
+    if (!p || !s || !u0_host) return fail(IPMCMC_EINVAL, "NULL argument");
+    if (n_chains <= 0) return fail(IPMCMC_EINVAL, "n_chains=%lld", (long long)n_chains);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int d = s->dim;
+    const size_t B = (size_t)n_chains;
+    const size_t nvar = p->model == IPMCMC_MODEL_LORENZ ? (size_t)p->l.nvar : 0;
+    if (nvar && !model_state_host) return fail(IPMCMC_EINVAL, "Lorenz needs model_state_host");
+    // one device arena: u | phi | count | mean | m2 | pooled | model_state | trace | counters(int64)
+    const size_t n_trace = samples_host ? B * (size_t)n_record * d : 0;
+    const size_t n_dbl = B * d + B + B + B * d + B * d + (2 * d + 7) + B * nvar + n_trace;
+    double *arena = nullptr;
+    CUDA_TRY(cudaMallocAsync((void **)&arena, n_dbl * sizeof(double) + B * CNT_N * sizeof(long long), st));
+    double *u = arena, *phi = u + B * d, *cnt = phi + B, *mean = cnt + B, *m2 = mean + B * d, *pooled = m2 + B * d;
+    double *mstate = pooled + (2 * d + 7), *trace = mstate + B * nvar;
+    long long *counters = (long long *)(trace + n_trace);
+    int rc = 0;
+    auto cleanup = [&](int code) {
+        cudaFreeAsync(arena, st);
+        return code;
+    };
+    cudaError_t e;
+    e = cudaMemcpyAsync(u, u0_host, B * d * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && nvar) e = cudaMemcpyAsync(mstate, model_state_host, B * nvar * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(cnt, 0, (B + 2 * B * d) * sizeof(double), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(counters, 0, B * CNT_N * sizeof(long long), st);
+    if (e != cudaSuccess) return cleanup(fail(IPMCMC_ECUDA, "host->device staging: %s", cudaGetErrorString(e)));
+    fill_kernel<<<148, 256, 0, st>>>(phi, (long long)B, nan(""));
+    ipmcmc_chain_buffers cb;
+    memset(&cb, 0, sizeof cb);
+    cb.u_dev = u;
+    cb.phi_dev = phi;
+    cb.model_state_dev = nvar ? mstate : nullptr;
+    cb.mom_count_dev = cnt;
+    cb.mom_mean_dev = mean;
+    cb.mom_m2_dev = m2;
+    cb.counters_dev = (int64_t *)counters;
+    cb.trace_dev = samples_host ? trace : nullptr;
+    cb.n_record = samples_host ? n_record : 0;
+    rc = ipmcmc_run(p, s, &cb, n_chains, n_steps, stream);
+    if (rc) return cleanup(rc);
+    rc = ipmcmc_pool_moments(n_chains, d, cnt, mean, m2, (const int64_t *)counters, pooled, stream);
+    if (rc) return cleanup(rc);
+    if (samples_host) e = cudaMemcpyAsync(samples_host, trace, n_trace * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && counters_host) e = cudaMemcpyAsync(counters_host, counters, B * CNT_N * sizeof(long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && pooled_host) e = cudaMemcpyAsync(pooled_host, pooled, (2 * d + 7) * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && nvar) e = cudaMemcpyAsync(model_state_host, mstate, B * nvar * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cleanup(fail(IPMCMC_ECUDA, "run/device->host: %s", cudaGetErrorString(e)));
+    return cleanup(0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// probes
+// ------------------------------------------------------------------------------------------------
+extern "C" int ipmcmc_lorenz_rhs(int32_t K, int32_t J, int64_t n, const double *theta_dev, const double *state_dev,
+                                 double *rhs_dev, void *stream) {
+    if (K < 1 || K > 32) return fail(IPMCMC_EUNSUPPORTED, "K=%d outside [1,32]", K);
+    if (n <= 0) return 0;
+    const int groups = lorenz_groups(K);
+    const long long blocks = (n + groups - 1) / groups;
+    LORENZ_DISPATCH(lorenz_rhs_kernel, J, <<<grid_for(blocks), 32, 0, (cudaStream_t)stream>>>(K, n, theta_dev, state_dev, rhs_dev));
+    return 0;
+}
+
+extern "C" int ipmcmc_lorenz_rk45_attempt(int32_t K, int32_t J, int64_t n, const double *theta_dev,
+                                          const double *state_dev, const double *h_dev, double rtol, double atol,
+                                          double *out_dev, void *stream) {
+    if (K < 1 || K > 32) return fail(IPMCMC_EUNSUPPORTED, "K=%d outside [1,32]", K);
+    if (n <= 0) return 0;
+    const int groups = lorenz_groups(K);
+    const long long blocks = (n + groups - 1) / groups;
+    LORENZ_DISPATCH(lorenz_attempt_kernel, J,
+                    <<<grid_for(blocks), 32, 0, (cudaStream_t)stream>>>(K, n, theta_dev, state_dev, h_dev, rtol, atol, out_dev));
+    return 0;
+}
+
+__global__ void rng_probe_kernel(unsigned long long seed, long long chain_offset, long long first_step,
+                                 long long n_chains, long long n_steps, int d, double *out) {
+    const long long total = n_chains * n_steps * (d + 1);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int slot = (int)(i % (d + 1));
+        const long long s = (i / (d + 1)) % n_steps, c = i / ((long long)(d + 1) * n_steps);
+        out[i] = slot < d ? draw_normal(seed, (uint64_t)(chain_offset + c), (uint64_t)(first_step + s), (uint32_t)slot)
+                          : draw_uniform(seed, (uint64_t)(chain_offset + c), (uint64_t)(first_step + s));
+    }
+}
+
+extern "C" int ipmcmc_rng_probe(uint64_t seed, int64_t chain_offset, int64_t first_step, int64_t n_chains,
+                                int64_t n_steps, int32_t dim, double *out_dev, void *stream) {
+    if (!out_dev || dim < 1) return fail(IPMCMC_EINVAL, "bad argument");
+    rng_probe_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(seed, chain_offset, first_step, n_chains, n_steps, dim, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Dependent-free DFMA throughput: 8 independent FMA chains per thread, 2048 threads per SM.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[0] = s;
+}
+
+extern "C" int ipmcmc_fp64_peak(int32_t iters, double *tflops_out) {
+    if (!tflops_out) return fail(IPMCMC_EINVAL, "NULL argument");
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *out;
+    CUDA_TRY(cudaMalloc((void **)&out, 8));
+    const int inner = 2048, blocks = sms * 8;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    dfma_peak_kernel<<<blocks, 256>>>(out, inner, 0.999999, 1e-9);  // warm-up
+    double best = 0.0;
+    for (int r = 0; r < (iters > 0 ? iters : 5); ++r) {
+        CUDA_TRY(cudaEventRecord(e0));
+        dfma_peak_kernel<<<blocks, 256>>>(out, inner, 0.999999, 1e-9);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8 * 16 * (double)inner * 256.0 * blocks;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops_out = best;
+    return 0;
+}

@@ -1,0 +1,269 @@
+// Two-scale Lorenz-96 + Dormand-Prince 5(4) with scipy's controller, laid out for the warp:
+// ONE LANE PER SLOW VARIABLE.  Lane k of a chain's lane group holds X_k and its J fast variables
+// Y_{k,0..J-1} in registers, so the fast-fast coupling (periodic WITHIN a block, lorenz.py:90-101),
+// the block mean and the slow->fast forcing are thread-local; only the three slow neighbours
+// X_{k-1}, X_{k-2}, X_{k+1} travel by shuffle (6 SHFL.32 per RHS instead of 14+ for a
+// lane-per-variable layout).  A chain occupies K lanes; floor(32/K) chains share a warp (5 chains
+// for the reference's K = 6) and step in lock-step through predicated attempts.
+//
+// Restates Lorenz96.__call__ (report/scripts/lorenz.py:44-101), moment_function
+// (report/scripts/lorenz_mcmc.py:17-40), LorenzObservationOperator (lorenz_mcmc.py:43-71) and
+// scipy.integrate.solve_ivp(method='RK45') with default tolerances (scipy/integrate/_ivp/rk.py:14-175,
+// common.py:63-140; call site lorenz_mcmc.py:70-71).  CPU statement: oracle/lorenz_np.py.
+#pragma once
+#include "common.cuh"
+
+namespace ipmcmc {
+
+struct LorenzDev {
+    int K, J, max_attempts, nvar;
+    double T, c, rtol, atol;
+    double param_mean[3];
+    PotentialDev pot;
+};
+
+// Dormand-Prince tableau (scipy rk.py RK45.A/B/C/E)
+#define DP_A21 (1.0 / 5)
+#define DP_A31 (3.0 / 40)
+#define DP_A32 (9.0 / 40)
+#define DP_A41 (44.0 / 45)
+#define DP_A42 (-56.0 / 15)
+#define DP_A43 (32.0 / 9)
+#define DP_A51 (19372.0 / 6561)
+#define DP_A52 (-25360.0 / 2187)
+#define DP_A53 (64448.0 / 6561)
+#define DP_A54 (-212.0 / 729)
+#define DP_A61 (9017.0 / 3168)
+#define DP_A62 (-355.0 / 33)
+#define DP_A63 (46732.0 / 5247)
+#define DP_A64 (49.0 / 176)
+#define DP_A65 (-5103.0 / 18656)
+#define DP_B1 (35.0 / 384)
+#define DP_B3 (500.0 / 1113)
+#define DP_B4 (125.0 / 192)
+#define DP_B5 (-2187.0 / 6784)
+#define DP_B6 (11.0 / 84)
+#define DP_E1 (-71.0 / 57600)
+#define DP_E3 (71.0 / 16695)
+#define DP_E4 (-71.0 / 1920)
+#define DP_E5 (17253.0 / 339200)
+#define DP_E6 (-22.0 / 525)
+#define DP_E7 (1.0 / 40)
+#define RK_SAFETY 0.9
+#define RK_MIN_FACTOR 0.2
+#define RK_MAX_FACTOR 10.0
+
+// Parameters of one chain's ODE, identical on all lanes of its group.
+struct LorenzTheta {
+    double F, h, c, b;
+};
+
+template <int J>
+struct LorenzLanes {
+    static constexpr int NV = J + 1;  // variables per lane: y[0] = X_k, y[1+j] = Y_{k,j}
+    int src_m1, src_m2, src_p1;       // absolute lane ids of X_{k-1}, X_{k-2}, X_{k+1}
+    int base, K, k;
+    bool valid;
+
+    __device__ __forceinline__ void init(int lane, int K_, int groups) {
+        K = K_;
+        const int g = lane / K_;
+        valid = g < groups;
+        base = valid ? g * K_ : 0;
+        k = valid ? lane - base : 0;
+        src_m1 = base + (k + K_ - 1) % K_;
+        src_m2 = base + (k + 2 * K_ - 2) % K_;
+        src_p1 = base + (k + 1) % K_;
+    }
+
+    // sum over the lanes of the group, same order on every lane (lane 0 first)
+    __device__ __forceinline__ double group_sum(double v) const {
+        double s = __shfl_sync(FULL, v, base);
+        for (int j = 1; j < K; ++j) s = s + __shfl_sync(FULL, v, base + j);
+        return s;
+    }
+
+    // d(state)/dt in the reference's rounding order (lorenz.py:73-101)
+    __device__ __forceinline__ void rhs(const LorenzTheta &th, const double (&y)[NV], double (&dy)[NV]) const {
+        const double X = y[0];
+        const double Xm1 = __shfl_sync(FULL, X, src_m1);
+        const double Xm2 = __shfl_sync(FULL, X, src_m2);
+        const double Xp1 = __shfl_sync(FULL, X, src_p1);
+        double out = -X;
+        out = out - (Xm1 * Xm2 - Xm1 * Xp1);
+        out = out + th.F;
+        if (J > 0) {
+            // np.average(Y_k): numpy pairwise sum (sequential for J < 8) / J
+            double s;
+            if (J < 8) {
+                s = -0.0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) s = s + y[1 + j];
+            } else {
+                s = np_pairwise_sum([&](int j) { return y[1 + j]; }, 0, J);
+            }
+            out = out - (th.h * th.c) * (s / (double)J);
+            const double hx = th.h / (double)J * X;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const double Yp1 = y[1 + (j + 1) % J], Yp2 = y[1 + (j + 2) % J], Ym1 = y[1 + (j + J - 1) % J];
+                double o = -y[1 + j];
+                o = o - th.b * (Yp1 * Yp2 - Ym1 * Yp1);
+                o = o + hx;
+                dy[1 + j] = o * th.c;
+            }
+        }
+        dy[0] = out;
+    }
+
+    // RMS norm over the chain's n = K*(J+1) variables of v/scale (scipy common.py:63-65)
+    __device__ __forceinline__ double rms(const double (&v)[NV], double inv_sqrt_n) const {
+        double ss = 0.0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) ss = fma(v[i], v[i], ss);
+        return sqrt(group_sum(ss)) * inv_sqrt_n;
+    }
+
+    // One Dormand-Prince attempt (scipy rk.py:14-72 + error norm :111-116).
+    // k1 = f(y) on entry; k7 = f(y_new) on exit.  Stage sums use FMA chains.
+    __device__ __forceinline__ double attempt(const LorenzTheta &th, const double (&y)[NV], const double (&k1)[NV],
+                                              double h, double rtol, double atol, double inv_sqrt_n,
+                                              double (&ynew)[NV], double (&k7)[NV]) const {
+        double k2[NV], k3[NV], k4[NV], k5[NV], k6[NV], ys[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) ys[i] = fma(DP_A21 * k1[i], h, y[i]);
+        rhs(th, ys, k2);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) ys[i] = fma(fma(DP_A32, k2[i], DP_A31 * k1[i]), h, y[i]);
+        rhs(th, ys, k3);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) ys[i] = fma(fma(DP_A43, k3[i], fma(DP_A42, k2[i], DP_A41 * k1[i])), h, y[i]);
+        rhs(th, ys, k4);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            ys[i] = fma(fma(DP_A54, k4[i], fma(DP_A53, k3[i], fma(DP_A52, k2[i], DP_A51 * k1[i]))), h, y[i]);
+        rhs(th, ys, k5);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            ys[i] = fma(fma(DP_A65, k5[i], fma(DP_A64, k4[i], fma(DP_A63, k3[i], fma(DP_A62, k2[i], DP_A61 * k1[i])))),
+                        h, y[i]);
+        rhs(th, ys, k6);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            ynew[i] = fma(h, fma(DP_B6, k6[i], fma(DP_B5, k5[i], fma(DP_B4, k4[i], fma(DP_B3, k3[i], DP_B1 * k1[i])))),
+                          y[i]);
+        rhs(th, ynew, k7);
+        double e[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const double err =
+                fma(DP_E7, k7[i], fma(DP_E6, k6[i], fma(DP_E5, k5[i], fma(DP_E4, k4[i], fma(DP_E3, k3[i], DP_E1 * k1[i]))))) * h;
+            const double scale = fma(absmax_bits(y[i], ynew[i]), rtol, atol);
+            e[i] = err / scale;
+        }
+        return rms(e, inv_sqrt_n);
+    }
+};
+
+// Per-chain integrator state for the lock-step solve.
+template <int J>
+struct LorenzSolve {
+    static constexpr int NV = J + 1;
+    double y[NV], f[NV];
+    double msum[5];  // running sums of [X, Y0, X^2, X*Y0, Y0^2] over stored states (lorenz_mcmc.py:17-40)
+    double t, h_abs;
+    int n_t, n_acc, n_rej;
+    bool done, step_rejected, new_step;
+
+    __device__ __forceinline__ void add_moments() {
+        const double X = y[0], Y0 = (J > 0) ? y[1] : 0.0;
+        msum[0] += X;
+        msum[1] += Y0;
+        msum[2] += X * X;
+        msum[3] += X * Y0;
+        msum[4] += Y0 * Y0;
+        ++n_t;
+    }
+
+    // solve_ivp(fun, (0,T), y0, 'RK45'): initial step (common.py:68-140), then steps until t == T.
+    // `active`: this lane's chain takes part (others run predicated-off). All 32 lanes must call.
+    __device__ __forceinline__ void solve(const LorenzLanes<J> &L, const LorenzDev &P, const LorenzTheta &th, bool active) {
+        const double inv_sqrt_n = 1.0 / sqrt((double)P.nvar);
+        t = 0.0;
+        n_t = n_acc = n_rej = 0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) msum[i] = 0.0;
+        L.rhs(th, y, f);
+        add_moments();  // t0 is stored too (lorenz_mcmc.py:68)
+        {   // select_initial_step, direction = +1, order = 4
+            double sc[NV], a0[NV], a1[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                sc[i] = fma(fabs(y[i]), P.rtol, P.atol);
+                a0[i] = y[i] / sc[i];
+                a1[i] = f[i] / sc[i];
+            }
+            const double d0 = L.rms(a0, inv_sqrt_n), d1 = L.rms(a1, inv_sqrt_n);
+            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+            h0 = fmin(h0, P.T);
+            double y1[NV], f1[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) y1[i] = fma(h0, f[i], y[i]);
+            L.rhs(th, y1, f1);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) a0[i] = (f1[i] - f[i]) / sc[i];
+            const double d2 = L.rms(a0, inv_sqrt_n) / h0;
+            double h1;
+            if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+            else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
+            h_abs = fmin(fmin(100.0 * h0, h1), P.T);
+        }
+        done = !active || !(P.T > 0.0);
+        step_rejected = false;
+        new_step = true;
+        int guard = 0;
+        while (__any_sync(FULL, !done)) {
+            // ---- RungeKutta._step_impl (rk.py:118-175), one attempt per iteration
+            const double t_next = __longlong_as_double(__double_as_longlong(t) + 1);  // nextafter(t, +inf), t >= 0
+            const double min_step = 10.0 * fabs(t_next - t);
+            if (new_step) {
+                if (h_abs < min_step) h_abs = min_step;
+                step_rejected = false;
+            }
+            bool fail = h_abs < min_step;  // TOO_SMALL_STEP: solve_ivp stops with what it has
+            double h = h_abs;
+            double t_new = t + h;
+            if (t_new - P.T > 0.0) t_new = P.T;
+            h = t_new - t;
+            const double h_abs_used = fabs(h);
+            double ynew[NV], fnew[NV];
+            const double err = L.attempt(th, y, f, h, P.rtol, P.atol, inv_sqrt_n, ynew, fnew);
+            if (!done && !fail) {
+                if (err < 1.0) {
+                    double factor = (err == 0.0) ? RK_MAX_FACTOR : fmin(RK_MAX_FACTOR, RK_SAFETY * pow(err, -0.2));
+                    if (step_rejected) factor = fmin(1.0, factor);
+                    h_abs = h_abs_used * factor;
+                    t = t_new;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) {
+                        y[i] = ynew[i];
+                        f[i] = fnew[i];
+                    }
+                    add_moments();
+                    ++n_acc;
+                    new_step = true;
+                    if (t == P.T) done = true;
+                } else {
+                    h_abs = h_abs_used * fmax(RK_MIN_FACTOR, RK_SAFETY * pow(err, -0.2));
+                    step_rejected = true;
+                    new_step = false;
+                    ++n_rej;   // NaN error norms land here too, as in scipy (nan < 1 is False)
+                }
+            }
+            ++guard;
+            if (fail || guard >= P.max_attempts) done = true;
+        }
+    }
+};
+
+}  // namespace ipmcmc

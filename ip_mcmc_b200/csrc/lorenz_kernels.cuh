@@ -1,0 +1,269 @@
+// Lorenz kernels: batched forward evaluation, the fused Metropolis kernel, and the RHS / single
+// RK-attempt probes used by the parity tests.  floor(32/K) chains per warp, one warp per CTA.
+#pragma once
+#include "lorenz.cuh"
+#include "sampler.cuh"
+
+namespace ipmcmc {
+
+// smem per CTA: (groups + 1 dummy) x (G[MAX_OBS] | r2[MAX_OBS])
+__host__ __device__ inline int lorenz_groups(int K) { return 32 / K; }
+__host__ __device__ inline size_t lorenz_smem_bytes(int K) {
+    return (size_t)(lorenz_groups(K) + 1) * 2 * IPMCMC_MAX_OBS * sizeof(double);
+}
+
+template <int J>
+__device__ __forceinline__ void lorenz_load_state(const LorenzLanes<J> &L, const double *s, double (&y)[J + 1]) {
+    y[0] = s[L.k];
+#pragma unroll
+    for (int j = 0; j < J; ++j) y[1 + j] = s[L.K + L.k * J + j];
+}
+template <int J>
+__device__ __forceinline__ void lorenz_store_state(const LorenzLanes<J> &L, double *s, const double (&y)[J + 1]) {
+    s[L.k] = y[0];
+#pragma unroll
+    for (int j = 0; j < J; ++j) s[L.K + L.k * J + j] = y[1 + j];
+}
+
+// LorenzObservationOperator.__call__ (lorenz_mcmc.py:55-68) + EvolutionPotential (potential.py:53-54)
+// for every chain of the warp at once.  `ui`: component i of the chain's u on group lane i.
+// S.y carries the initial condition in and the end state out (lorenz_mcmc.py:66).
+template <int J>
+__device__ __noinline__ double lorenz_phi(const LorenzLanes<J> &L, const LorenzDev &P, double ui, LorenzSolve<J> &S,
+                                          bool active, double *Gs, double *r2) {
+    // F, h, b = prior_means + u   (lorenz_mcmc.py:64)
+    const double pi = (L.k < 3) ? P.param_mean[L.k] + ui : 0.0;
+    LorenzTheta th;
+    th.F = __shfl_sync(FULL, pi, L.base + 0);
+    th.h = __shfl_sync(FULL, pi, L.base + 1);
+    th.b = __shfl_sync(FULL, pi, L.base + 2);
+    th.c = P.c;
+    double ykeep[J + 1];
+#pragma unroll
+    for (int i = 0; i < J + 1; ++i) ykeep[i] = S.y[i];
+    S.solve(L, P, th, active);
+    if (!active) {  // an inactive chain keeps its state
+#pragma unroll
+        for (int i = 0; i < J + 1; ++i) S.y[i] = ykeep[i];
+    }
+    // np.mean(moment_function(y), axis=1)   (lorenz_mcmc.py:68)
+    const double nt = (double)S.n_t;
+#pragma unroll
+    for (int m = 0; m < 5; ++m) Gs[m * L.K + L.k] = S.msum[m] / nt;
+    __syncwarp();
+    return potential_from_G(P.pot, Gs, r2, L.k, L.K, FULL);
+}
+
+template <int J>
+__global__ void __launch_bounds__(32) lorenz_forward_kernel(const __grid_constant__ LorenzDev P, long long n,
+                                                            const double *__restrict__ u, double *__restrict__ G,
+                                                            double *__restrict__ phi, double *__restrict__ state,
+                                                            long long *__restrict__ work) {
+    extern __shared__ double smem[];
+    const int lane = lane_id();
+    const int groups = lorenz_groups(P.K);
+    LorenzLanes<J> L;
+    L.init(lane, P.K, groups);
+    const int slot = L.valid ? lane / P.K : groups;
+    double *Gs = smem + (size_t)slot * 2 * IPMCMC_MAX_OBS, *r2 = Gs + IPMCMC_MAX_OBS;
+    for (long long c0 = (long long)blockIdx.x * groups; c0 < n; c0 += (long long)gridDim.x * groups) {
+        const long long c = c0 + slot;
+        const bool active = L.valid && c < n;
+        LorenzSolve<J> S;
+#pragma unroll
+        for (int i = 0; i < J + 1; ++i) S.y[i] = 0.0;
+        if (active) lorenz_load_state<J>(L, state + c * P.nvar, S.y);
+        const double ui = (active && L.k < 3) ? u[c * 3 + L.k] : 0.0;
+        const double ph = lorenz_phi<J>(L, P, ui, S, active, Gs, r2);
+        if (active) {
+            lorenz_store_state<J>(L, state + c * P.nvar, S.y);
+            if (G)
+                for (int i = L.k; i < P.pot.q; i += P.K) G[c * P.pot.q + i] = Gs[i];
+            if (L.k == 0) {
+                if (phi) phi[c] = ph;
+                if (work) {
+                    work[2 * c] = S.n_acc;
+                    work[2 * c + 1] = S.n_rej;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int J>
+__global__ void __launch_bounds__(32) lorenz_chain_kernel(const __grid_constant__ LorenzDev P,
+                                                          const __grid_constant__ SamplerDev Sd,
+                                                          const __grid_constant__ ChainBufDev C, long long n_chains,
+                                                          long long n_steps) {
+    extern __shared__ double smem[];
+    const int lane = lane_id();
+    const int groups = lorenz_groups(P.K);
+    LorenzLanes<J> L;
+    L.init(lane, P.K, groups);
+    const int slot = L.valid ? lane / P.K : groups;
+    double *Gs = smem + (size_t)slot * 2 * IPMCMC_MAX_OBS, *r2 = Gs + IPMCMC_MAX_OBS;
+    const Group Gp{L.base, P.K, L.k, FULL};
+    const int d = Sd.d;  // 3
+    for (long long c0 = (long long)blockIdx.x * groups; c0 < n_chains; c0 += (long long)gridDim.x * groups) {
+        const long long c = c0 + slot;
+        const bool active = L.valid && c < n_chains;
+        const long long cs = active ? c : 0;  // safe index for predicated-off lanes
+        const long long cg = Sd.chain_offset + cs;
+        const bool own = active && L.k < d;
+        LorenzSolve<J> S;
+#pragma unroll
+        for (int i = 0; i < J + 1; ++i) S.y[i] = 0.0;
+        if (active) lorenz_load_state<J>(L, C.model_state + c * P.nvar, S.y);
+        double ui = own ? C.u[c * d + L.k] : 0.0;
+        double phi_u = active ? C.phi[c] : 0.0;
+        long long cnt[CNT_N];
+#pragma unroll
+        for (int k = 0; k < CNT_N; ++k) cnt[k] = 0;
+        double reg_u = (Sd.accepter == IPMCMC_ACCEPT_RW) ? prior_regulariser(Sd, Gp, ui) : 0.0;
+        Welford mom{active ? C.mom_count[c] : 0.0, own ? C.mom_mean[c * d + L.k] : 0.0,
+                    own ? C.mom_m2[c * d + L.k] : 0.0};
+        long long n_rec = 0;
+
+        for (long long s = 0; s < n_steps; ++s) {
+            const long long gstep = Sd.first_step + s;
+            double ca, cb;
+            step_coefs(Sd, gstep, ca, cb);
+            const double w = proposal_noise(Sd, C, Gp, cs, cg, s, n_steps, gstep);
+            const double vi = ca * ui + cb * w;
+            if (C.vlog && own) C.vlog[(c * n_steps + s) * d + L.k] = vi;
+            const bool ok = active && (!Sd.has_constraint || constraint_ok(Sd, Gp, vi));
+            // The reference evaluates Phi(u) and then Phi(v) every step, each solve starting where
+            // the previous one ended (accepter.py:121-122 + lorenz_mcmc.py:66).
+            const bool need_u = ok && (Sd.recompute_phi_u || isnan(phi_u));
+            if (__any_sync(FULL, need_u)) {
+                const double ph = lorenz_phi<J>(L, P, ui, S, need_u, Gs, r2);
+                if (need_u) {
+                    phi_u = ph;
+                    cnt[CNT_WORK_A] += S.n_acc;
+                    cnt[CNT_WORK_B] += S.n_rej;
+                }
+            }
+            const double ph_v = lorenz_phi<J>(L, P, vi, S, ok, Gs, r2);
+            bool accepted = false;
+            double phi_v = nan(""), a = nan("");
+            int work = 0;
+            if (ok) {
+                phi_v = ph_v;
+                work = S.n_acc + S.n_rej;
+                cnt[CNT_WORK_A] += S.n_acc;
+                cnt[CNT_WORK_B] += S.n_rej;
+            }
+            double reg_v = 0.0;
+            if (Sd.accepter == IPMCMC_ACCEPT_RW) reg_v = prior_regulariser(Sd, Gp, vi);
+            if (ok) {
+                a = exp((phi_u + reg_u) - (phi_v + reg_v));
+                const double U = C.inject_u ? C.inject_u[c * n_steps + s]
+                                            : draw_uniform(Sd.seed, (uint64_t)cg, (uint64_t)gstep);
+                accepted = a > U;
+                if (!isfinite(phi_v)) cnt[CNT_NONFINITE] += 1;
+                if (accepted) {
+                    ui = vi;
+                    phi_u = phi_v;
+                    reg_u = reg_v;
+                }
+            } else if (active) {
+                cnt[CNT_CONSTRAINT] += 1;
+            }
+            cnt[CNT_CALLS] += 1;
+            cnt[CNT_ACCEPTS] += accepted ? 1 : 0;
+            if (C.steplog && active && L.k == 0) {
+                double *Lg = C.steplog + (c * n_steps + s) * 4;
+                Lg[0] = phi_v;
+                Lg[1] = a;
+                Lg[2] = accepted ? 1.0 : 0.0;
+                Lg[3] = (double)work;
+            }
+            if (Sd.record_interval > 0 && gstep >= Sd.record_start &&
+                ((gstep - Sd.record_start + 1) % Sd.record_interval) == 0) {
+                mom.add(ui);
+                if (C.trace && n_rec < C.n_record && own) C.trace[(c * C.n_record + n_rec) * d + L.k] = ui;
+                ++n_rec;
+            }
+        }
+        if (active) {
+            lorenz_store_state<J>(L, C.model_state + c * P.nvar, S.y);
+            if (own) {
+                C.u[c * d + L.k] = ui;
+                C.mom_mean[c * d + L.k] = mom.mean;
+                C.mom_m2[c * d + L.k] = mom.m2;
+            }
+            if (L.k == 0) {
+                C.phi[c] = phi_u;
+                C.mom_count[c] = mom.count;
+#pragma unroll
+                for (int k = 0; k < CNT_N; ++k) C.counters[c * CNT_N + k] += cnt[k];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- probes -------------------------------------------------------------------------------
+template <int J>
+__global__ void __launch_bounds__(32) lorenz_rhs_kernel(int K, long long n, const double *__restrict__ theta,
+                                                        const double *__restrict__ state, double *__restrict__ out) {
+    const int lane = lane_id();
+    const int groups = lorenz_groups(K);
+    const int nvar = K * (J + 1);
+    LorenzLanes<J> L;
+    L.init(lane, K, groups);
+    const int slot = L.valid ? lane / K : groups;
+    for (long long c0 = (long long)blockIdx.x * groups; c0 < n; c0 += (long long)gridDim.x * groups) {
+        const long long c = c0 + slot;
+        const bool active = L.valid && c < n;
+        double y[J + 1], dy[J + 1];
+#pragma unroll
+        for (int i = 0; i < J + 1; ++i) y[i] = 0.0;
+        LorenzTheta th{0, 0, 0, 0};
+        if (active) {
+            lorenz_load_state<J>(L, state + c * nvar, y);
+            th = LorenzTheta{theta[4 * c], theta[4 * c + 1], theta[4 * c + 2], theta[4 * c + 3]};
+        }
+        L.rhs(th, y, dy);
+        if (active) lorenz_store_state<J>(L, out + c * nvar, dy);
+    }
+}
+
+template <int J>
+__global__ void __launch_bounds__(32) lorenz_attempt_kernel(int K, long long n, const double *__restrict__ theta,
+                                                            const double *__restrict__ state,
+                                                            const double *__restrict__ hstep, double rtol, double atol,
+                                                            double *__restrict__ out) {
+    const int lane = lane_id();
+    const int groups = lorenz_groups(K);
+    const int nvar = K * (J + 1);
+    LorenzLanes<J> L;
+    L.init(lane, K, groups);
+    const int slot = L.valid ? lane / K : groups;
+    const double inv_sqrt_n = 1.0 / sqrt((double)nvar);
+    for (long long c0 = (long long)blockIdx.x * groups; c0 < n; c0 += (long long)gridDim.x * groups) {
+        const long long c = c0 + slot;
+        const bool active = L.valid && c < n;
+        double y[J + 1], f[J + 1], yn[J + 1], fn[J + 1];
+#pragma unroll
+        for (int i = 0; i < J + 1; ++i) y[i] = 0.0;
+        LorenzTheta th{0, 0, 0, 0};
+        double h = 0.0;
+        if (active) {
+            lorenz_load_state<J>(L, state + c * nvar, y);
+            th = LorenzTheta{theta[4 * c], theta[4 * c + 1], theta[4 * c + 2], theta[4 * c + 3]};
+            h = hstep[c];
+        }
+        L.rhs(th, y, f);
+        const double err = L.attempt(th, y, f, h, rtol, atol, inv_sqrt_n, yn, fn);
+        if (active) {
+            double *o = out + c * (2 * nvar + 1);
+            lorenz_store_state<J>(L, o, yn);
+            lorenz_store_state<J>(L, o + nvar, fn);
+            if (L.k == 0) o[2 * nvar] = err;
+        }
+    }
+}
+
+}  // namespace ipmcmc

@@ -1,0 +1,119 @@
+"""MCMCSampler with the reference's interface (ip_mcmc/ip_mcmc/sampler.py:6-54), driving the
+fused CUDA Metropolis kernel instead of a Python loop.
+
+    sampler = MCMCSampler(proposer, accepter, rng)
+    samples = sampler.run(u_0, n_samples, burn_in=1000, sample_interval=200)      # [n_samples, d]
+    samples = sampler.run(u_0, n_samples, 0, 1, n_chains=4096)                    # [4096, n_samples, d]
+
+Differences that are inherent to batching (documented in DESIGN.md):
+  * randomness comes from Philox4x32-10 streams keyed by (seed, global chain id); the seed is
+    drawn from `rng` (one `rng.integers` call), so a run is reproducible from the rng's seed;
+  * nothing is printed per sample (the reference prints a line per sample, sampler.py:24).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from . import accepter as _acc
+from . import stats as _stats
+from .engine import ChainBatch, SamplerSpec, F64
+from .potential import EvolutionPotential
+from .proposer import _GaussianStepProposer
+
+
+class MCMCSampler:
+    def __init__(self, proposal, acceptance, rng):
+        self.proposer = proposal
+        self.accepter = acceptance
+        self.rng = rng
+        self.last_run = None
+
+    # ---- compilation of the object graph ------------------------------------------------------
+    def _compile(self, total_steps, burn_in, sample_interval, recompute_phi_u):
+        if not isinstance(self.proposer, _GaussianStepProposer):
+            raise TypeError("proposer %r has no device implementation" % (self.proposer,))
+        a = _acc.device_spec(self.accepter)
+        pot = a["potential"]
+        if not isinstance(pot, EvolutionPotential):
+            raise TypeError("the accepter's potential must be an EvolutionPotential over a device forward "
+                            "model (no CPU fallback)")
+        p = self.proposer.device_spec(total_steps)
+        prior_cov_dist = self.proposer.w
+        d = prior_cov_dist.k
+        chol = None
+        if a["kind"] == _lib.ACCEPT_RW:
+            chol = a["prior"].L
+            if chol.shape != (d, d):
+                raise ValueError("prior dimension mismatch between proposer and accepter")
+        if recompute_phi_u is None:
+            recompute_phi_u = pot.G.stateful       # reference order for the stateful Lorenz operator
+        seed = int(self.rng.integers(0, 2 ** 63 - 1)) if hasattr(self.rng, "integers") else int(self.rng)
+        spec = SamplerSpec(dim=d, proposer_kind=p["kind"], accepter_kind=a["kind"], coef_u=p["coef_u"],
+                           coef_w=p["coef_w"], schedule=p["schedule"], factor=prior_cov_dist.sample_factor(),
+                           prior_chol=chol, constraint=a["constraint"], recompute_phi_u=recompute_phi_u,
+                           seed=seed, record_start=max(0, burn_in - sample_interval),
+                           record_interval=sample_interval)
+        return spec, pot, a
+
+    def run(self, u_0, n_samples, burn_in=1000, sample_interval=200, n_chains=None, chain_offset=0,
+            steps_per_launch=None, return_device=False, recompute_phi_u=None):
+        """Same step accounting as the reference (sampler.py:18-28): max(0, burn_in - interval)
+        unrecorded steps, then n_samples * interval steps recording every interval-th state.
+
+        Returns ndarray [n_samples, d] for a single chain (u_0 of shape (d,), n_chains None) or
+        [n_chains, n_samples, d] for a batch.  Statistics of the run are left in `self.last_run`.
+        """
+        if sample_interval < 1:
+            raise ValueError("sample_interval must be >= 1")
+        pre = max(0, burn_in - sample_interval)
+        total = pre + n_samples * sample_interval
+        spec, pot, a = self._compile(total, burn_in, sample_interval, recompute_phi_u)
+        if isinstance(self.accepter, _acc.CountedAccepter):
+            self.accepter.reset()                   # only when outermost (sampler.py:15-16)
+        problem = pot.problem()
+        single = n_chains is None and np.ndim(u_0) == 1
+        chains = ChainBatch(problem, u_0, n_chains=n_chains, chain_offset=chain_offset)
+        trace = torch.empty((chains.n, n_samples, chains.d), dtype=F64, device=problem.device)
+        if steps_per_launch is None or steps_per_launch >= total:
+            chains.run(spec, total, trace=trace)
+        else:
+            # chunked launches: each chunk records into its slice of the trace
+            def recorded_before(x):          # samples recorded by global steps < x
+                return max(0, x - pre) // sample_interval
+
+            done = 0
+            while done < total:
+                n = min(steps_per_launch, total - done)
+                r0, r1 = recorded_before(done), recorded_before(done + n)
+                sub = None
+                if r1 > r0:
+                    sub = torch.empty((chains.n, r1 - r0, chains.d), dtype=F64, device=problem.device)
+                chains.run(spec, n, trace=sub)
+                if sub is not None:
+                    trace[:, r0:r1] = sub
+                done += n
+        pooled = chains.pooled()
+        counters = chains.counters
+        if pot.G.stateful and single:
+            pot.G.IC = chains.model_state[0].cpu().numpy()
+        pooled_h = pooled.cpu().numpy()
+        d = chains.d
+        self.last_run = dict(n_chains=chains.n, total_steps=total, launches=chains.launches,
+                             pooled_count=pooled_h[0], pooled_mean=pooled_h[1:1 + d],
+                             pooled_var=pooled_h[1 + d:1 + 2 * d] / max(pooled_h[0] - 1, 1),
+                             counters=dict(zip(ChainBatch.COUNTER_NAMES, pooled_h[1 + 2 * d:].astype(np.int64))),
+                             per_chain_counters=counters, chains=chains, seed=spec.seed,
+                             h2d_bytes=chains.h2d_bytes)
+        c = a["counted"]
+        if c is not None:
+            c.calls += int(self.last_run["counters"]["calls"])
+            c.accepts += int(self.last_run["counters"]["accepts"])
+        if return_device:
+            return trace[0] if single else trace
+        out = trace.cpu().numpy()
+        self.last_run["d2h_bytes"] = out.nbytes + pooled_h.nbytes
+        return out[0] if single else out
+
+    @classmethod
+    def autocorr(cls, x):
+        return _stats.autocorr(x)

@@ -1,0 +1,195 @@
+"""GPU parity of the fused Metropolis kernel: the reference's own chains (recorded with a noise
+tape, tests/golden/chain_*.npz) replayed with injected noise must be reproduced state by state."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import burgers_np as B
+from oracle import mcmc_np as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_common
+    return gpu_common
+
+
+def _spec(kind, g, prior, **kw):
+    import ip_mcmc_b200 as M
+    from ip_mcmc_b200 import _lib
+    if kind == "pcn":
+        beta = float(g["beta"])
+        return M.SamplerSpec(3, _lib.PROPOSE_PCN, _lib.ACCEPT_PCN, coef_u=np.sqrt(1 - beta ** 2), coef_w=beta, **kw)
+    delta = float(g["delta"])
+    return M.SamplerSpec(3, _lib.PROPOSE_RW, _lib.ACCEPT_RW, coef_u=1.0, coef_w=np.sqrt(2 * delta),
+                         prior_chol=prior.L, **kw)
+
+
+@pytest.mark.parametrize("name,kind", [("chain_burgers_pcn_N64.npz", "pcn"), ("chain_burgers_pcn_N128.npz", "pcn"),
+                                       ("chain_burgers_rw_N64.npz", "rw")])
+def test_replay_reference_chain(G, name, kind):
+    g = golden(name)
+    f, pot, prior, _ = G.burgers_setup(int(g["N"]))
+    states, slog, vlog, ch = G.run_injected(pot, _spec(kind, g, prior), g["u0"], g["normals"], g["uniforms"], n_copies=3)
+    for c in range(3):
+        assert np.array_equal(states[c], g["samples"])
+        assert np.array_equal(vlog[c], g["v"])
+        assert np.array_equal(slog[c, :, 0], g["phi_v"])
+        assert int(slog[c, :, 2].sum()) == int(g["accepts"])
+    cnt = ch.counters.cpu().numpy()
+    assert np.all(cnt[:, 0] == int(g["calls"])) and np.all(cnt[:, 1] == int(g["accepts"]))
+    assert np.all(cnt[:, 3] == len(g["normals"]) + 1)      # one solve per step + Phi(u_0)
+    # accept probabilities vs the oracle's exp (device exp is <= 1 ulp from libm)
+    a_ref = np.exp(g["phi_u"] - g["phi_v"]) if kind == "pcn" else None
+    if a_ref is not None:
+        np.testing.assert_allclose(slog[0, :, 1], a_ref, rtol=1e-14)
+
+
+def test_recompute_phi_u_is_bit_equivalent_for_burgers(G):
+    """The reference evaluates Phi(u) again every step (accepter.py:121-122); for a deterministic
+    G caching is bit-equivalent -- checked by running the kernel both ways."""
+    g = golden("chain_burgers_pcn_N64.npz")
+    f, pot, prior, _ = G.burgers_setup(64)
+    s1, l1, _, c1 = G.run_injected(pot, _spec("pcn", g, prior), g["u0"], g["normals"], g["uniforms"])
+    s2, l2, _, c2 = G.run_injected(pot, _spec("pcn", g, prior, recompute_phi_u=True), g["u0"], g["normals"], g["uniforms"])
+    assert np.array_equal(s1, s2) and np.array_equal(l1[..., :3], l2[..., :3])
+    assert c2.counters[0, 3].item() == 2 * len(g["normals"]) + 1   # the reference's 2 solves per step
+
+
+def test_replay_varstep_schedule(G):
+    """VarStepStandardRWProposer with the PWLinear schedule (proposer.py:33-56, burgers_beta.py:131-147)."""
+    import ip_mcmc_b200 as M
+    from ip_mcmc_b200 import _lib
+    g = golden("chain_burgers_varstep_rw_N64.npz")
+    f, pot, prior, _ = G.burgers_setup(64)
+    sched = np.stack([np.ones(len(g["schedule"])), np.sqrt(2) * np.sqrt(g["schedule"])], axis=1)
+    spec = M.SamplerSpec(3, _lib.PROPOSE_RW, _lib.ACCEPT_RW, schedule=sched, prior_chol=prior.L)
+    states, slog, _, ch = G.run_injected(pot, spec, g["u0"], g["normals"], g["uniforms"])
+    assert np.array_equal(states[0], g["samples"])
+    assert ch.counters[0, 1].item() == int(g["accepts"])
+
+
+def test_replay_constrained_chain(G):
+    """ConstrainAccepter: a violated box rejects WITHOUT consuming a uniform (accepter.py:52-55)."""
+    import ip_mcmc_b200 as M
+    from ip_mcmc_b200 import _lib
+    g = golden("chain_burgers_constrained_rw_N64.npz")
+    f, pot, prior, _ = G.burgers_setup(64)
+    lo, hi = float(g["lo"]), float(g["hi"])
+    box = M.BoxConstraint([-np.inf, -np.inf, lo], [np.inf, np.inf, hi], shift=[0, 0, -0.5])
+    # expand the tape: the reference drew U only on the steps whose proposal satisfied the box
+    P = B.BurgersProblem(64)
+    opot = O.Potential(P, P.G_params(G.TRUTH), G.NOISE_COV)
+    ref = O.run_chain(opot, g["u0"], g["normals"], g["uniforms"], O.RW, O.RW, float(g["delta"]),
+                      prior_cov=G.PRIOR_COV, constraint=lambda v: lo < v[2] - 0.5 < hi)
+    assert np.array_equal(ref["u"], g["samples"])
+    valid = ~np.isnan(ref["a"])
+    U = np.full(len(g["normals"]), 0.5)
+    U[valid] = g["uniforms"]
+    spec = M.SamplerSpec(3, _lib.PROPOSE_RW, _lib.ACCEPT_RW, coef_u=1.0, coef_w=np.sqrt(2 * float(g["delta"])),
+                         prior_chol=prior.L, constraint=box)
+    states, slog, _, ch = G.run_injected(pot, spec, g["u0"], g["normals"], U)
+    assert np.array_equal(states[0], g["samples"])
+    cnt = ch.counters[0].cpu().numpy()
+    assert cnt[0] == int(g["calls"]) and cnt[1] == int(g["accepts"])
+    assert cnt[5] == (~valid).sum() and cnt[3] == valid.sum() + 1   # no solve on constrained steps
+
+
+def test_sampler_api_step_accounting_and_counters(G):
+    """MCMCSampler.run keeps the reference's accounting (sampler.py:12-33, sampler_test.py:8-18):
+    max(0, burn_in - interval) + n*interval calls, counter reset when outermost, shapes."""
+    import ip_mcmc_b200 as M
+    f, pot, prior, _ = G.burgers_setup(32)
+    acc = M.CountedAccepter(M.pCNAccepter(pot))
+    s = M.MCMCSampler(M.ConstSteppCNProposer(0.25, prior), acc, np.random.default_rng(2))
+    out = s.run(np.zeros(3), 27, burn_in=20, sample_interval=10)
+    assert out.shape == (27, 3) and acc.calls == 280
+    assert 0 < acc.accepts < 280 and acc.ratio() == acc.accepts / 280
+    out = s.run(np.zeros(3), 5, 0, 1, n_chains=7)
+    assert out.shape == (7, 5, 3) and acc.calls == 35          # reset, then 7 chains x 5 steps
+    assert s.last_run["counters"]["work_b"] == 7 * 6
+    with pytest.raises(TypeError):
+        M.EvolutionPotential(lambda u: u, np.zeros(5), None)     # no CPU fallback for Python G
+    with pytest.raises(TypeError):
+        M.MCMCSampler(M.ConstSteppCNProposer(0.25, prior), M.ConstrainAccepter(M.pCNAccepter(pot), lambda v: True),
+                      np.random.default_rng(0)).run(np.zeros(3), 1, 0, 1)
+
+
+def test_recording_moments_and_chunked_launches(G):
+    """Thinning/burn-in slicing matches the reference definition; on-device Welford moments equal
+    the moments of the recorded trace; chunked launches and one launch give identical chains."""
+    import ip_mcmc_b200 as M
+    f, pot, prior, _ = G.burgers_setup(32)
+    mk = lambda: M.MCMCSampler(M.ConstSteppCNProposer(0.25, prior), M.CountedAccepter(M.pCNAccepter(pot)),
+                               np.random.default_rng(5))
+    s_all = mk()
+    every = s_all.run(np.zeros(3), 130, 0, 1, n_chains=16)
+    s_thin = mk()
+    thin = s_thin.run(np.zeros(3), 12, burn_in=20, sample_interval=10, n_chains=16)
+    assert np.array_equal(thin, O.samples_from_states(every.transpose(1, 0, 2), 12, 20, 10).transpose(1, 0, 2))
+    s_chunk = mk()
+    chunk = s_chunk.run(np.zeros(3), 12, burn_in=20, sample_interval=10, n_chains=16, steps_per_launch=17)
+    assert np.array_equal(chunk, thin) and s_chunk.last_run["launches"] > 3
+    lr = s_thin.last_run
+    flat = thin.reshape(-1, 3)
+    assert lr["pooled_count"] == flat.shape[0]
+    np.testing.assert_allclose(lr["pooled_mean"], flat.mean(0), rtol=1e-12)
+    np.testing.assert_allclose(lr["pooled_var"], flat.var(0, ddof=1), rtol=1e-10)
+
+
+def test_results_do_not_depend_on_sharding(G):
+    """Philox is keyed by the GLOBAL chain id: 12 chains in one batch == 3 shards of 4."""
+    import ip_mcmc_b200 as M
+    f, pot, prior, _ = G.burgers_setup(32)
+    mk = lambda: M.MCMCSampler(M.ConstStepStandardRWProposer(0.01, prior), M.StandardRWAccepter(pot, prior),
+                               np.random.default_rng(9))
+    whole = mk().run(np.zeros(3), 40, 0, 1, n_chains=12)
+    parts = [mk().run(np.zeros(3), 40, 0, 1, n_chains=4, chain_offset=4 * r) for r in range(3)]
+    assert np.array_equal(whole, np.concatenate(parts, axis=0))
+    assert not np.array_equal(whole[0], whole[1])
+
+
+def test_engine_rng_matches_cpu_statement(G):
+    from ip_mcmc_b200 import _lib
+    from oracle import philox_np as P
+    lib = _lib.load()
+    seed = 2 + (5 << 32)
+    out = torch.empty((3, 40, 4), dtype=torch.float64, device="cuda")
+    _lib.check(lib.ipmcmc_rng_probe(seed, 7, (1 << 33) + 5, 3, 40, 3, out.data_ptr(), None))
+    o = out.cpu().numpy()
+    for c in range(3):
+        z, U = P.chain_noise(seed, 7 + c, (1 << 33) + 5, 40, 3)
+        assert np.array_equal(o[c, :, 3], U)                    # integers -> uniforms: bit exact
+        np.testing.assert_allclose(o[c, :, :3], z, rtol=0, atol=1e-13)   # log/sqrt/cos: few ulp
+
+
+def test_free_running_chain_statistics_vs_cpu_oracle(G):
+    """Statistical parity: acceptance rate and posterior mean of
+    free-running device chains vs CPU oracle chains, within Monte Carlo error."""
+    import ip_mcmc_b200 as M
+    N, beta, n_steps, burn = 32, 0.25, 600, 200
+    f, pot, prior, y = G.burgers_setup(N)
+    s = M.MCMCSampler(M.ConstSteppCNProposer(beta, prior), M.CountedAccepter(M.pCNAccepter(pot)), np.random.default_rng(2))
+    dev = s.run(np.zeros(3), n_steps, 0, 1, n_chains=256)
+    P = B.BurgersProblem(N)
+    opot = O.Potential(P, y, G.NOISE_COV)
+    rng = np.random.default_rng(3)
+    cpu_states, cpu_acc = [], []
+    for c in range(6):
+        z = 0.25 * rng.standard_normal((n_steps, 3))
+        r = O.run_chain(opot, np.zeros(3), z, rng.random(n_steps), O.PCN, O.PCN, beta)
+        cpu_states.append(r["u"][burn:])
+        cpu_acc.append(r["accepted"][burn:].mean())
+    cpu = np.concatenate(cpu_states)
+    dev_post = dev[:, burn:].reshape(-1, 3)
+    # device: 256 chains x 400 steps; cpu: 6 x 400.  MCSE dominated by the CPU side.
+    ess_cpu = sum(M.stats.ess(st).min() for st in cpu_states)
+    mcse = cpu.std(0) / np.sqrt(max(ess_cpu, 4))
+    assert np.all(np.abs(dev_post.mean(0) - cpu.mean(0)) < 5 * mcse + 1e-3), (dev_post.mean(0), cpu.mean(0), mcse)
+    acc_dev = s.last_run["per_chain_counters"][:, 1].double().mean().item() / n_steps
+    assert abs(acc_dev - np.mean(cpu_acc)) < 0.12
+    # posterior concentrates near the truth (noise-free data), far from the prior mean start
+    assert np.all(np.abs(dev_post.mean(0) - (G.TRUTH - G.PRIOR_MEAN)) < 0.15)

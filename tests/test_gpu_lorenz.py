@@ -1,0 +1,168 @@
+"""GPU parity of the Lorenz-96 path.  Parity is pinned at the RHS (bit-exact), the single
+Dormand-Prince attempt and short horizons; over T = 20 any two roundings of the same algorithm
+diverge (positive Lyapunov exponent), so long solves are compared statistically (SURVEY.md
+section 7 'Lorenz chaos')."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import lorenz_np as L
+from oracle import mcmc_np as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_common
+    return gpu_common
+
+
+def _lorenz_setup(T, p=None):
+    import ip_mcmc_b200 as M
+    p = golden("lorenz_problem_K6_J4.npz") if p is None else p
+    f = M.Lorenz96Moments(6, 4, T, 1, p["prior_means"], p["IC"])
+    noise = M.GaussianDistribution(np.zeros(30), 0.5 ** 2 * np.diag(p["var"]))     # lorenz_mcmc.py:111-112
+    prior = M.GaussianDistribution(np.zeros(3), np.diag([10., 1, 10]))            # lorenz_mcmc.py:115,119
+    pot = M.EvolutionPotential(f, p["y"], noise)
+    return f, pot, prior, p
+
+
+def test_rhs_bit_identical_to_reference(G):
+    from ip_mcmc_b200 import _lib
+    lib = _lib.load()
+    g = golden("lorenz_rhs.npz")
+    for i in range(int(g["n_cases"])):
+        K, J = int(g[f"case{i}_K"]), int(g[f"case{i}_J"])
+        n = 11          # more states than fit one warp: exercises group packing and the tail
+        th = G.cuda(np.tile([float(g[f"case{i}_{k}"]) for k in "Fhcb"], (n, 1)))
+        st = G.cuda(np.tile(g[f"case{i}_state"], (n, 1)))
+        out = torch.empty_like(st)
+        _lib.check(lib.ipmcmc_lorenz_rhs(K, J, n, th.data_ptr(), st.data_ptr(), out.data_ptr(), None))
+        o = out.cpu().numpy()
+        assert all(np.array_equal(o[k], g[f"case{i}_rhs"]) for k in range(n)), (K, J)
+
+
+def test_reference_rhs_known_answers(G):
+    """lorenz.py:114-147 (K >= 1 supported by the probe)."""
+    from ip_mcmc_b200 import _lib
+    lib = _lib.load()
+    cases = [((4, 1), (0, 0, 0, 0), [1, 2, 3, 4, 0, 0, 0, 0], [-5, -3, 3, -7, 0, 0, 0, 0]),
+             ((1, 4), (0, 0, 1, 2), [0, 1, 2, 3, 4], [0, 3, -20, 5, -2]),
+             ((1, 2), (0, 2, -1, 0), [0, 1, 2], [3, 1, 2]),
+             ((2, 2), (1, 1, 1, 1), [2, 3, 4, 5, 6, 7], [-2.5, -10.5, 2, -8, 2.5, -11.5]),
+             ((3, 1), (2, 1, 1, 1), [0, 0, 0, 0, 0, 0], [2, 2, 2, 0, 0, 0])]
+    for (K, J), th, s, want in cases:
+        tht, st = G.cuda([th]), G.cuda([s])
+        out = torch.empty_like(st)
+        _lib.check(lib.ipmcmc_lorenz_rhs(K, J, 1, tht.data_ptr(), st.data_ptr(), out.data_ptr(), None))
+        np.testing.assert_allclose(out.cpu().numpy()[0], want, rtol=1e-15, atol=1e-15)
+
+
+def test_single_rk45_attempt_vs_scipy_restatement(G):
+    """One Dormand-Prince attempt: y_new, f_new and the RMS error norm against oracle/lorenz_np.py
+    (bit-identical to scipy).  Device stage sums are FMA chains, scipy's are BLAS dots: agreement
+    to 1e-12 relative (north_star 1e-10)."""
+    from ip_mcmc_b200 import _lib
+    lib = _lib.load()
+    p = golden("lorenz_problem_K6_J4.npz")
+    K, J = 6, 4
+    rng = np.random.default_rng(4)
+    n = 13
+    thetas = np.column_stack([rng.uniform(8, 12, n), rng.uniform(8, 12, n), np.ones(n), rng.uniform(8, 12, n)])
+    states = p["IC"] + 0.1 * rng.standard_normal((n, 30))
+    hs = 10 ** rng.uniform(-3, -1.3, n)
+    out = torch.empty((n, 61), dtype=torch.float64, device="cuda")
+    tht, st, ht = G.cuda(thetas), G.cuda(states), G.cuda(hs)
+    _lib.check(lib.ipmcmc_lorenz_rk45_attempt(K, J, n, tht.data_ptr(), st.data_ptr(), ht.data_ptr(), 1e-3, 1e-6,
+                                              out.data_ptr(), None))
+    o = out.cpu().numpy()
+    for i in range(n):
+        fun = lambda t, s: L.lorenz_rhs(s, K, J, *thetas[i])
+        yn, fn, err, _ = L.rk45_attempt(fun, 0.0, states[i], fun(0, states[i]), hs[i])
+        np.testing.assert_allclose(o[i, :30], yn, rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(o[i, 30:60], fn, rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(o[i, 60], err, rtol=1e-9)
+
+
+def test_short_solves_vs_reference(G):
+    """solve_ivp parity while chaos has not yet amplified rounding: same accepted/rejected step
+    counts (controller decisions) and G / end state close to the reference's."""
+    gs = golden("lorenz_solves.npz")
+    for i in range(int(gs["n_cases"])):
+        T = float(gs[f"case{i}_T"])
+        if T > 2:
+            continue
+        f, pot, _, p = _lorenz_setup(T)
+        r = f.batch(gs[f"case{i}_u"].reshape(1, 3), p["IC"].reshape(1, -1))
+        acc, rej = r["work"][0].tolist()
+        assert acc == int(gs[f"case{i}_n_t"]) - 1
+        assert 2 + 6 * (acc + rej) == int(gs[f"case{i}_nfev"])
+        tol = {0.25: 1e-11, 1.0: 1e-8, 2.0: 1e-4}[T]       # e^(lambda T) growth of 1e-16 seeds
+        np.testing.assert_allclose(r["G"].cpu().numpy()[0], gs[f"case{i}_G"], rtol=tol, atol=tol)
+        np.testing.assert_allclose(r["state"].cpu().numpy()[0], gs[f"case{i}_IC_end"], rtol=0, atol=100 * tol)
+
+
+def test_stateful_operator_and_potential_semantics(G):
+    """LorenzObservationOperator carries its IC (lorenz_mcmc.py:66): two successive calls differ
+    and equal one solve continued from the first end state; Phi matches the oracle's logpdf."""
+    f, pot, _, p = _lorenz_setup(0.25)
+    u = np.array([-1.9, 1.9, 0.9])
+    op = L.LorenzProblem(6, 4, 0.25, 1, p["prior_means"], p["IC"])
+    opot = O.Potential(op, p["y"], 0.25 * np.diag(p["var"]))
+    for _ in range(3):
+        g_dev, g_ref = f(u), op(u)
+        np.testing.assert_allclose(g_dev, g_ref, rtol=1e-9)
+        np.testing.assert_allclose(f.IC, op.IC, rtol=0, atol=1e-9)
+    f2, pot2, _, _ = _lorenz_setup(0.25)
+    op2 = L.LorenzProblem(6, 4, 0.25, 1, p["prior_means"], p["IC"])
+    opot2 = O.Potential(op2, p["y"], 0.25 * np.diag(p["var"]))
+    for _ in range(2):
+        np.testing.assert_allclose(pot2(u), opot2(u), rtol=1e-9)
+
+
+def test_long_solves_statistically(G):
+    """T = 20 (the reference's setting): G(u) is a noisy time average; device and reference
+    realisations must agree within the natural variability, and step counts within a few %."""
+    gs = golden("lorenz_solves.npz")
+    for i in range(int(gs["n_cases"])):
+        T = float(gs[f"case{i}_T"])
+        if T < 20:
+            continue
+        f, pot, _, p = _lorenz_setup(T)
+        n = 64
+        ic = p["IC"] + 1e-9 * np.random.default_rng(i).standard_normal((n, 30))   # decorrelated realisations
+        r = f.batch(np.tile(gs[f"case{i}_u"], (n, 1)), ic)
+        Gd = r["G"].cpu().numpy()
+        sd = Gd.std(0) + 1e-12
+        z = np.abs(gs[f"case{i}_G"] - Gd.mean(0)) / sd
+        assert np.all(z < 5), z.max()        # the reference realisation is a typical member
+        acc = r["work"][:, 0].double().mean().item()
+        assert abs(acc - (int(gs[f"case{i}_n_t"]) - 1)) < 0.08 * acc
+
+
+def test_lorenz_chain_first_steps_and_statistics(G):
+    """Reference chain (pCN beta=0.5, T=2) replayed with injected noise: proposals are bit-identical
+    while decisions agree; Phi of the first step agrees closely (before chaos decorrelates the
+    carried IC).  Then free-running chains: acceptance in the reference's ballpark."""
+    import ip_mcmc_b200 as M
+    from ip_mcmc_b200 import _lib
+    g = golden("chain_lorenz_pcn_T2.npz")
+    f, pot, prior, p = _lorenz_setup(float(g["T"]))
+    beta = float(g["beta"])
+    spec = M.SamplerSpec(3, _lib.PROPOSE_PCN, _lib.ACCEPT_PCN, coef_u=np.sqrt(1 - beta ** 2), coef_w=beta,
+                         recompute_phi_u=True)
+    states, slog, vlog, ch = G.run_injected(pot, spec, g["u0"], g["normals"], g["uniforms"], n_copies=7)
+    assert np.all(states == states[0]) and np.all(slog == slog[0])        # lanes groups agree
+    assert np.array_equal(vlog[0, 0], g["v"][0])
+    np.testing.assert_allclose(slog[0, 0, 0], g["phi_v"][0], rtol=1e-5)
+    same = np.cumprod(np.all(states[0] == g["samples"], axis=1)).sum()
+    assert same >= 1          # identical decisions until chaos flips a borderline accept
+    # free-running: 2 solves per step (Phi(u) then Phi(v)), counters consistent
+    s = M.MCMCSampler(M.ConstSteppCNProposer(beta, prior), M.CountedAccepter(M.pCNAccepter(pot)), np.random.default_rng(1))
+    out = s.run(g["u0"], 30, 0, 1, n_chains=33)
+    assert out.shape == (33, 30, 3)
+    acc = s.accepter.ratio()
+    assert 0.25 < acc < 0.9, acc          # reference: 24/40 at T=2, "around 0.6" at T=20 (lorenz.org:277-279)
+    assert s.last_run["counters"]["work_a"] > 33 * 30 * 2 * 50
