@@ -14,7 +14,7 @@ SOURCES = ["engine.cu"]
 HEADERS = ["common.cuh", "philox.cuh", "burgers.cuh", "burgers_kernels.cuh", "lorenz.cuh",
            "lorenz_kernels.cuh", "sampler.cuh", os.path.join("..", "..", "include", "ipmcmc.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",
-              "-std=c++17", "--extended-lambda", "-shared", "-Xcompiler", "-fPIC"]
+              "-std=c++17", "--extended-lambda", "--split-compile=0", "-shared", "-Xcompiler", "-fPIC"]
 
 
 def _stale():

@@ -29,13 +29,13 @@ __device__ __forceinline__ void burgers_measure(const BurgersDev &B, const doubl
 
 // G(u) and Phi(u) for the parameter vector whose component i sits on lane i (value `ui`).
 // Leaves the end state in smem `state` and G in `Gs`.  Returns Phi; n_fv by reference.
-template <int CPL, int NUMERICS>
+template <int CPL, int NUMERICS, bool PADDED>
 __device__ __noinline__ double burgers_phi(const BurgersDev &B, double ui, double *state, double *Gs, double *r2,
                                               int lane, int &n_fv) {
     // FVMObservationOperator.__call__ (utilities.py:40-41): IC(u_0 + u)
     const double pi = (lane < B.d) ? B.param_mean[lane] + ui : 0.0;
     const double p0 = shfl(pi, 0), p1 = shfl(pi, 1), p2 = shfl(pi, 2);
-    BurgersWarp<CPL, NUMERICS> W;
+    BurgersWarp<CPL, NUMERICS, PADDED> W;
     n_fv = W.integrate(B, p0, p1, p2, lane);
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
@@ -44,10 +44,12 @@ __device__ __noinline__ double burgers_phi(const BurgersDev &B, double ui, doubl
     }
     __syncwarp();
     burgers_measure(B, state, Gs, lane);
-    return potential_from_G(B.pot, Gs, r2, lane, 32, FULL);
+    const double phi = potential_from_G(B.pot, Gs, r2, lane, 32, FULL);
+    // a solve stopped by the safety cap has not reached T: report it as non-finite (-> rejected)
+    return W.capped ? nan("") : phi;
 }
 
-template <int CPL, int NUMERICS>
+template <int CPL, int NUMERICS, bool PADDED>
 __global__ void __launch_bounds__(32) burgers_forward_kernel(const __grid_constant__ BurgersDev B, long long n,
                                                              const double *__restrict__ u, double *__restrict__ G,
                                                              double *__restrict__ phi, double *__restrict__ state_out,
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(32) burgers_forward_kernel(const __grid_consta
     for (long long c = blockIdx.x; c < n; c += gridDim.x) {
         const double ui = (lane < B.d) ? u[c * B.d + lane] : 0.0;
         int n_fv;
-        const double ph = burgers_phi<CPL, NUMERICS>(B, ui, state, Gs, r2, lane, n_fv);
+        const double ph = burgers_phi<CPL, NUMERICS, PADDED>(B, ui, state, Gs, r2, lane, n_fv);
         if (G)
             for (int i = lane; i < B.pot.q; i += 32) G[c * B.pot.q + i] = Gs[i];
         if (state_out)
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(32) burgers_forward_kernel(const __grid_consta
     }
 }
 
-template <int CPL, int NUMERICS>
+template <int CPL, int NUMERICS, bool PADDED>
 __global__ void __launch_bounds__(32) burgers_chain_kernel(const __grid_constant__ BurgersDev B,
                                                            const __grid_constant__ SamplerDev S,
                                                            const __grid_constant__ ChainBufDev C, long long n_chains,
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(32) burgers_chain_kernel(const __grid_constant
         for (int k = 0; k < CNT_N; ++k) cnt[k] = 0;
         int n_fv;
         if (isnan(phi_u)) {  // first launch: Phi(u_0) not known yet
-            phi_u = burgers_phi<CPL, NUMERICS>(B, ui, state, Gs, r2, lane, n_fv);
+            phi_u = burgers_phi<CPL, NUMERICS, PADDED>(B, ui, state, Gs, r2, lane, n_fv);
             cnt[CNT_WORK_A] += n_fv;
             cnt[CNT_WORK_B] += 1;
         }
@@ -116,11 +118,11 @@ __global__ void __launch_bounds__(32) burgers_chain_kernel(const __grid_constant
             if (ok) {
                 if (S.recompute_phi_u) {  // the reference's 2 solves per step (accepter.py:121-122)
                     int nf0;
-                    phi_u = burgers_phi<CPL, NUMERICS>(B, ui, state, Gs, r2, lane, nf0);
+                    phi_u = burgers_phi<CPL, NUMERICS, PADDED>(B, ui, state, Gs, r2, lane, nf0);
                     cnt[CNT_WORK_A] += nf0;
                     cnt[CNT_WORK_B] += 1;
                 }
-                phi_v = burgers_phi<CPL, NUMERICS>(B, vi, state, Gs, r2, lane, n_fv);
+                phi_v = burgers_phi<CPL, NUMERICS, PADDED>(B, vi, state, Gs, r2, lane, n_fv);
                 cnt[CNT_WORK_A] += n_fv;
                 cnt[CNT_WORK_B] += 1;
                 double reg_v = 0.0;

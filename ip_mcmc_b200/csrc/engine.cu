@@ -175,35 +175,41 @@ extern "C" int ipmcmc_lorenz_create(const ipmcmc_lorenz_desc *d, ipmcmc_problem 
 // ------------------------------------------------------------------------------------------------
 static int grid_for(long long n_blocks) { return (int)(n_blocks < 2147483647LL ? n_blocks : 2147483647LL); }
 
-template <int CPL, int NUM>
+template <int CPL, int NUM, bool PAD>
 static int burgers_launch_forward(ipmcmc_problem *p, long long n, const double *u, double *G, double *phi,
                                   double *state, long long *work, cudaStream_t st) {
     const size_t smem = burgers_smem_bytes(p->b.N);
-    burgers_forward_kernel<CPL, NUM><<<grid_for(n), 32, smem, st>>>(p->b, n, u, G, phi, state, work);
+    burgers_forward_kernel<CPL, NUM, PAD><<<grid_for(n), 32, smem, st>>>(p->b, n, u, G, phi, state, work);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-template <int CPL, int NUM>
+template <int CPL, int NUM, bool PAD>
 static int burgers_launch_chain(ipmcmc_problem *p, const SamplerDev &S, const ChainBufDev &C, long long n_chains,
                                 long long n_steps, cudaStream_t st) {
     const size_t smem = burgers_smem_bytes(p->b.N);
-    burgers_chain_kernel<CPL, NUM><<<grid_for(n_chains), 32, smem, st>>>(p->b, S, C, n_chains, n_steps);
+    burgers_chain_kernel<CPL, NUM, PAD><<<grid_for(n_chains), 32, smem, st>>>(p->b, S, C, n_chains, n_steps);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
+#define BURGERS_CASE(FN, C, ...)                                                                        \
+    case C:                                                                                             \
+        if (fused) return padded ? FN<C, NUM_FUSED, true>(__VA_ARGS__) : FN<C, NUM_FUSED, false>(__VA_ARGS__); \
+        return padded ? FN<C, NUM_EXACT, true>(__VA_ARGS__) : FN<C, NUM_EXACT, false>(__VA_ARGS__);
 
 #define BURGERS_DISPATCH(FN, ...)                                                       \
     do {                                                                                \
         const int cpl = pick_cpl(p->b.N);                                               \
         const bool fused = p->numerics == IPMCMC_NUMERICS_FUSED;                        \
+        const bool padded = p->b.N != 32 * cpl;                                         \
         switch (cpl) {                                                                  \
-            case 1: return fused ? FN<1, NUM_FUSED>(__VA_ARGS__) : FN<1, NUM_EXACT>(__VA_ARGS__);   \
-            case 2: return fused ? FN<2, NUM_FUSED>(__VA_ARGS__) : FN<2, NUM_EXACT>(__VA_ARGS__);   \
-            case 4: return fused ? FN<4, NUM_FUSED>(__VA_ARGS__) : FN<4, NUM_EXACT>(__VA_ARGS__);   \
-            case 7: return fused ? FN<7, NUM_FUSED>(__VA_ARGS__) : FN<7, NUM_EXACT>(__VA_ARGS__);   \
-            case 8: return fused ? FN<8, NUM_FUSED>(__VA_ARGS__) : FN<8, NUM_EXACT>(__VA_ARGS__);   \
-            case 16: return fused ? FN<16, NUM_FUSED>(__VA_ARGS__) : FN<16, NUM_EXACT>(__VA_ARGS__); \
-            case 32: return fused ? FN<32, NUM_FUSED>(__VA_ARGS__) : FN<32, NUM_EXACT>(__VA_ARGS__); \
+            BURGERS_CASE(FN, 1, __VA_ARGS__)                                            \
+            BURGERS_CASE(FN, 2, __VA_ARGS__)                                            \
+            BURGERS_CASE(FN, 4, __VA_ARGS__)                                            \
+            BURGERS_CASE(FN, 7, __VA_ARGS__)                                            \
+            BURGERS_CASE(FN, 8, __VA_ARGS__)                                            \
+            BURGERS_CASE(FN, 16, __VA_ARGS__)                                           \
+            BURGERS_CASE(FN, 32, __VA_ARGS__)                                           \
         }                                                                               \
         return fail(IPMCMC_EUNSUPPORTED, "no kernel for n_cells=%d", p->b.N);           \
     } while (0)

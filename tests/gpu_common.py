@@ -11,9 +11,9 @@ PRIOR_COV = 0.25 ** 2 * np.identity(3)
 NOISE_COV = 0.05 ** 2 * np.identity(5)
 
 
-def burgers_setup(N, numerics="exact", y=None):
+def burgers_setup(N, numerics="exact", y=None, max_fv_steps=0):
     """The reference's Burgers inverse problem (burgers_mcmc.py:22-123) on the device."""
-    f = M.BurgersFVM(N=N, numerics=numerics)
+    f = M.BurgersFVM(N=N, numerics=numerics, max_fv_steps=max_fv_steps)
     if y is None:
         y = f.at_parameters(TRUTH)                 # noise-free data G(u*) (burgers_mcmc.py:116)
     noise = M.GaussianDistribution(np.zeros(5), NOISE_COV)

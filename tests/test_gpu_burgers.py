@@ -51,9 +51,11 @@ def test_forward_random_parameters_vs_oracle(G, N):
     n = 24 if N <= 256 else 6
     u = 0.25 * rng.standard_normal((n, 3))
     u[0] = [0.3, -0.2, 1.49]       # jump right at the right boundary: ghost/IC edge case
-    u[1] = [0.3, -0.2, -0.49]      # jump at the left boundary
+    u[1] = [0.3, -0.2, -0.49]      # jump at the left boundary: the left ghost is faster than the
+    #                                interior-only CFL allows (rusanov.py:102-109) -> the scheme blows up
+    #                                and needs ~100x more steps; lift the engine's safety cap to follow it
     P = B.BurgersProblem(N)
-    f, pot, _, y = G.burgers_setup(N, "exact")
+    f, pot, _, y = G.burgers_setup(N, "exact", max_fv_steps=10 ** 6)
     assert np.array_equal(y, P.G_params(G.TRUTH))
     opot = O.Potential(P, y, G.NOISE_COV)
     r = pot.problem().forward(u, want_state=True)
@@ -82,6 +84,8 @@ def test_step_cap_and_nonfinite_are_reported(G):
     f = M.BurgersFVM(N=64, max_fv_steps=7)
     r = f.batch(np.zeros((3, 3)))
     assert r["work"][:, 0].tolist() == [7, 7, 7]
+    pot = M.EvolutionPotential(f, np.zeros(5), M.GaussianDistribution(np.zeros(5), np.identity(5)))
+    assert torch.isnan(pot.batch(np.zeros((2, 3)))["phi"]).all()      # capped solve -> non-finite Phi -> reject
     # an all-zero initial state gives dt = inf and a NaN state, as in the reference (0.5*dx/0)
     f = M.BurgersFVM(N=64)
     r = f.batch(np.array([[-1.0 - 1.5, -0.25, 0.0]]))     # left = 1 + p0 = 0, right = 0

