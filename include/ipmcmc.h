@@ -195,6 +195,14 @@ typedef struct ipmcmc_chain_buffers {
     /* optional IN: injected noise (parity mode; the reference's MockRNG seam)                  */
     const double *inject_w_dev; /* [n_chains, n_steps, d] proposal normals at the w level       */
     const double *inject_u_dev; /* [n_chains, n_steps]    accept uniforms                       */
+    /* optional scheduling hint (Burgers; results do not depend on it): the kernel runs
+       `warps_per_cta` chains per CTA (one warp each; 0 = library default) and warp w of CTA b
+       serves chain slot_chain_dev[b*warps_per_cta + w] (-1 = idle slot; NULL = identity).
+       Warps w and w+4 of a CTA share an SM sub-partition, so a caller that knows which chains
+       are expensive can pair heavy with light ones (ChainBatch does, from last launch's work). */
+    const int32_t *slot_chain_dev; /* [n_slots]                                                  */
+    int32_t n_slots;
+    int32_t warps_per_cta;
 } ipmcmc_chain_buffers;
 
 int ipmcmc_run(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, const ipmcmc_chain_buffers *b,

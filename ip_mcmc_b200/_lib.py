@@ -52,7 +52,8 @@ class ChainBuffers(C.Structure):
                 ("mom_count_dev", C.c_void_p), ("mom_mean_dev", C.c_void_p), ("mom_m2_dev", C.c_void_p),
                 ("counters_dev", C.c_void_p), ("trace_dev", C.c_void_p), ("n_record", C.c_int64),
                 ("steplog_dev", C.c_void_p), ("vlog_dev", C.c_void_p), ("inject_w_dev", C.c_void_p),
-                ("inject_u_dev", C.c_void_p)]
+                ("inject_u_dev", C.c_void_p), ("slot_chain_dev", C.c_void_p), ("n_slots", C.c_int32),
+                ("warps_per_cta", C.c_int32)]
 
 
 # every symbol include/ipmcmc.h declares

@@ -9,7 +9,9 @@
 namespace ipmcmc {
 
 // shared memory layout per warp: state[N] | G[MAX_OBS] | r2[MAX_OBS]
-__host__ __device__ inline size_t burgers_smem_bytes(int N) { return (size_t)(N + 2 * IPMCMC_MAX_OBS) * sizeof(double); }
+__host__ __device__ inline size_t burgers_smem_bytes(int N, int warps = 1) {
+    return (size_t)warps * (N + 2 * IPMCMC_MAX_OBS) * sizeof(double);
+}
 
 // Measurer.__call__ (utilities.py:100-109): m_i = 10 * trapz(values[l:r], dx) with numpy's
 // evaluation (dx*(y[1:]+y[:-1])/2.0).sum() in pairwise order; lane i handles window i.
@@ -50,14 +52,16 @@ __device__ __noinline__ double burgers_phi(const BurgersDev &B, double ui, doubl
 }
 
 template <int CPL, int NUMERICS, bool PADDED>
-__global__ void __launch_bounds__(32) burgers_forward_kernel(const __grid_constant__ BurgersDev B, long long n,
-                                                             const double *__restrict__ u, double *__restrict__ G,
-                                                             double *__restrict__ phi, double *__restrict__ state_out,
-                                                             long long *__restrict__ work) {
-    extern __shared__ double smem[];
+__global__ void __launch_bounds__(256) burgers_forward_kernel(const __grid_constant__ BurgersDev B, long long n,
+                                                              const double *__restrict__ u, double *__restrict__ G,
+                                                              double *__restrict__ phi, double *__restrict__ state_out,
+                                                              long long *__restrict__ work) {
+    extern __shared__ double smem_all[];
+    const int warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    double *smem = smem_all + (size_t)warp * (B.N + 2 * IPMCMC_MAX_OBS);
     double *state = smem, *Gs = smem + B.N, *r2 = Gs + IPMCMC_MAX_OBS;
     const int lane = lane_id();
-    for (long long c = blockIdx.x; c < n; c += gridDim.x) {
+    for (long long c = (long long)blockIdx.x * wpc + warp; c < n; c += (long long)gridDim.x * wpc) {
         const double ui = (lane < B.d) ? u[c * B.d + lane] : 0.0;
         int n_fv;
         const double ph = burgers_phi<CPL, NUMERICS, PADDED>(B, ui, state, Gs, r2, lane, n_fv);
@@ -76,17 +80,24 @@ __global__ void __launch_bounds__(32) burgers_forward_kernel(const __grid_consta
     }
 }
 
+// W warps per CTA, one chain per warp.  Warps never synchronise with each other; the CTA shape
+// only pins which chains share an SM sub-partition (warp w -> SMSP w % 4).
 template <int CPL, int NUMERICS, bool PADDED>
-__global__ void __launch_bounds__(32) burgers_chain_kernel(const __grid_constant__ BurgersDev B,
-                                                           const __grid_constant__ SamplerDev S,
-                                                           const __grid_constant__ ChainBufDev C, long long n_chains,
-                                                           long long n_steps) {
-    extern __shared__ double smem[];
+__global__ void __launch_bounds__(256) burgers_chain_kernel(const __grid_constant__ BurgersDev B,
+                                                            const __grid_constant__ SamplerDev S,
+                                                            const __grid_constant__ ChainBufDev C, long long n_chains,
+                                                            long long n_steps) {
+    extern __shared__ double smem_all[];
+    const int warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    double *smem = smem_all + (size_t)warp * (B.N + 2 * IPMCMC_MAX_OBS);
     double *state = smem, *Gs = smem + B.N, *r2 = Gs + IPMCMC_MAX_OBS;
     const int lane = lane_id();
     const Group Gp{0, 32, lane, FULL};
     const int d = S.d;
-    for (long long c = blockIdx.x; c < n_chains; c += gridDim.x) {
+    const long long n_slots = C.slot_chain ? (long long)C.n_slots : n_chains;
+    for (long long slot = (long long)blockIdx.x * wpc + warp; slot < n_slots; slot += (long long)gridDim.x * wpc) {
+        const long long c = C.slot_chain ? (long long)C.slot_chain[slot] : slot;
+        if (c < 0 || c >= n_chains) continue;
         const long long cg = S.chain_offset + c;
         double ui = (lane < d) ? C.u[c * d + lane] : 0.0;
         double phi_u = C.phi[c];

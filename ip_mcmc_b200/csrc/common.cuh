@@ -18,22 +18,27 @@ __device__ __forceinline__ double shfl(double v, int src, unsigned mask = FULL) 
 __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(FULL, v, 1); }
 __device__ __forceinline__ double shfl_down1(double v) { return __shfl_down_sync(FULL, v, 1); }
 
-// max over the warp of non-negative doubles (|u|): IEEE-754 ordering of non-negative doubles
-// equals the ordering of their bit patterns, so the reduction runs on the integer REDUX unit
-// (2 x CREDUX.MAX) instead of 5 shuffle+DSETP rounds on the fp64 pipe.
-__device__ __forceinline__ double warp_max_nonneg(double v) {
-    const uint64_t b = (uint64_t)__double_as_longlong(v);
-    const uint32_t hi = (uint32_t)(b >> 32), lo = (uint32_t)b;
+// |x| as an ordered 64-bit integer key: IEEE-754 ordering of non-negative doubles equals the
+// ordering of their bit patterns.  Kept in integer registers on purpose -- a round trip through
+// double makes the compiler re-materialise fabs as a DADD on the (precious) fp64 pipe.
+__device__ __forceinline__ uint64_t abs_key(double v) {
+    return ((uint64_t)((uint32_t)__double2hiint(v) & 0x7fffffffu) << 32) | (uint32_t)__double2loint(v);
+}
+__device__ __forceinline__ uint64_t key_max(uint64_t a, uint64_t b) { return a > b ? a : b; }
+
+// max over the warp of 64-bit keys on the integer REDUX unit (2 x CREDUX.MAX) instead of 5
+// shuffle + DSETP rounds on the fp64 pipe.
+__device__ __forceinline__ double warp_max_key(uint64_t k) {
+    const uint32_t hi = (uint32_t)(k >> 32), lo = (uint32_t)k;
     const uint32_t mh = __reduce_max_sync(FULL, hi);
     const uint32_t ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
-    return __longlong_as_double((long long)(((uint64_t)mh << 32) | ml));
+    return __hiloint2double((int)mh, (int)ml);
 }
 
 // max(|a|,|b|) for doubles through the integer pipe (keeps the fp64 pipe for arithmetic).
 __device__ __forceinline__ double absmax_bits(double a, double b) {
-    const uint64_t x = (uint64_t)__double_as_longlong(a) & 0x7fffffffffffffffull;
-    const uint64_t y = (uint64_t)__double_as_longlong(b) & 0x7fffffffffffffffull;
-    return __longlong_as_double((long long)(x > y ? x : y));
+    const uint64_t m = key_max(abs_key(a), abs_key(b));
+    return __hiloint2double((int)(m >> 32), (int)(uint32_t)m);
 }
 
 // NumPy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, @TYPE@_pairwise_sum) of

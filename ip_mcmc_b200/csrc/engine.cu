@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -178,16 +179,25 @@ static int grid_for(long long n_blocks) { return (int)(n_blocks < 2147483647LL ?
 template <int CPL, int NUM, bool PAD>
 static int burgers_launch_forward(ipmcmc_problem *p, long long n, const double *u, double *G, double *phi,
                                   double *state, long long *work, cudaStream_t st) {
-    const size_t smem = burgers_smem_bytes(p->b.N);
-    burgers_forward_kernel<CPL, NUM, PAD><<<grid_for(n), 32, smem, st>>>(p->b, n, u, G, phi, state, work);
+    // one chain per warp; CTAs of 4 warps (one per SM sub-partition) unless the batch is tiny
+    int wpc = n >= 4 * 148 ? 4 : 1;
+    if (const char *e = getenv("IPMCMC_FWD_WPC")) wpc = atoi(e) > 0 && atoi(e) <= 8 ? atoi(e) : wpc;  // experiments
+    const size_t smem = burgers_smem_bytes(p->b.N, wpc);
+    auto kern = burgers_forward_kernel<CPL, NUM, PAD>;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid_for((n + wpc - 1) / wpc), 32 * wpc, smem, st>>>(p->b, n, u, G, phi, state, work);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
 template <int CPL, int NUM, bool PAD>
 static int burgers_launch_chain(ipmcmc_problem *p, const SamplerDev &S, const ChainBufDev &C, long long n_chains,
-                                long long n_steps, cudaStream_t st) {
-    const size_t smem = burgers_smem_bytes(p->b.N);
-    burgers_chain_kernel<CPL, NUM, PAD><<<grid_for(n_chains), 32, smem, st>>>(p->b, S, C, n_chains, n_steps);
+                                long long n_steps, int wpc, cudaStream_t st) {
+    const size_t smem = burgers_smem_bytes(p->b.N, wpc);
+    auto kern = burgers_chain_kernel<CPL, NUM, PAD>;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long slots = C.slot_chain ? (long long)C.n_slots : n_chains;
+    kern<<<grid_for((slots + wpc - 1) / wpc), 32 * wpc, smem, st>>>(p->b, S, C, n_chains, n_steps);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -319,8 +329,13 @@ extern "C" int ipmcmc_run(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, const
     C.vlog = b->vlog_dev;
     C.inject_w = b->inject_w_dev;
     C.inject_u = b->inject_u_dev;
+    C.slot_chain = b->slot_chain_dev;
+    C.n_slots = b->n_slots;
     if (p->model == IPMCMC_MODEL_BURGERS) {
-        BURGERS_DISPATCH(burgers_launch_chain, p, S, C, n_chains, n_steps, st);
+        int wpc = b->warps_per_cta > 0 ? b->warps_per_cta : 4;
+        if (wpc > 8) return fail(IPMCMC_EINVAL, "warps_per_cta=%d > 8", wpc);
+        if (b->slot_chain_dev && b->n_slots < 1) return fail(IPMCMC_EINVAL, "slot_chain_dev without n_slots");
+        BURGERS_DISPATCH(burgers_launch_chain, p, S, C, n_chains, n_steps, wpc, st);
     }
     const int groups = lorenz_groups(p->l.K);
     const long long blocks = (n_chains + groups - 1) / groups;

@@ -35,6 +35,8 @@ struct ChainBufDev {
     long long n_record;
     double *steplog, *vlog;
     const double *inject_w, *inject_u;
+    const int *slot_chain;
+    int n_slots;
 };
 
 enum : int { CNT_CALLS = 0, CNT_ACCEPTS, CNT_WORK_A, CNT_WORK_B, CNT_NONFINITE, CNT_CONSTRAINT, CNT_N };

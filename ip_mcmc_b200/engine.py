@@ -126,6 +126,46 @@ class Problem:
         return dict(G=G, phi=phi, work=work, state=st)
 
 
+class Placement:
+    """Work-aware placement of chains on SM sub-partitions for SMALL batches (one wave).
+
+    With n <= 8 * n_SM chains the fused Burgers kernel runs one CTA of W = ceil(n / n_SM) warps per
+    SM, one chain per warp; warps w and w+4 of a CTA share a sub-partition (and its fp64 pipe).
+    Solve lengths are data dependent (FV steps ~ max|w| * N), so the launch lasts as long as the
+    most loaded sub-partition.  Before each launch the chains are ranked by the work they did in
+    the previous launch (a good predictor: states move slowly) and dealt out so that the heaviest
+    chains sit alone and the remaining heavy ones share with the lightest.  Pure scheduling: the
+    results do not depend on it (Philox is keyed by the chain id, not by the slot)."""
+
+    def __init__(self, n, n_sm, device):
+        self.W = min(8, -(-n // n_sm)) if n <= 8 * n_sm else 1
+        self.active = self.W > 4
+        if not self.active:
+            return
+        W, d = self.W, self.W - 4                      # d double bins (slots j, j+4), 4-d singles
+        n_cta = -(-n // W)
+        n_s, n_d = n_cta * (4 - d), n_cta * d
+        r = np.arange(n_cta * W)
+        slot = np.empty_like(r)
+        rs = r[:n_s]
+        slot[:n_s] = (rs // (4 - d)) * W + d + rs % (4 - d) if d < 4 else 0
+        b = np.arange(n_d)
+        slot[n_s:n_s + n_d] = (b // d) * W + b % d
+        b2 = n_d - 1 - b
+        slot[n_s + n_d:] = (b2 // d) * W + b2 % d + 4
+        assert np.array_equal(np.sort(slot), r)
+        self.n_slots = n_cta * W
+        self.slot_of_rank = torch.as_tensor(slot[:n], dtype=torch.int64).to(device)
+        self.slot_chain = torch.full((self.n_slots,), -1, dtype=torch.int32, device=device)
+
+    def update(self, work):
+        """work: cuda tensor [n] (any dtype) -- larger = more expensive."""
+        ranks = torch.argsort(work.to(torch.float64), descending=True)
+        self.slot_chain.fill_(-1)
+        self.slot_chain[self.slot_of_rank] = ranks.to(torch.int32)
+        return self.slot_chain
+
+
 class ChainBatch:
     """State of `n_chains` independent chains on the device (u, Phi(u), carried model state,
     Welford moments, counters)."""
@@ -173,6 +213,11 @@ class ChainBatch:
         self.step = 0
         self._keep = []
         self.launches = 0
+        self.placement = None
+        self._work_prev = None
+        if problem.kind == _lib.MODEL_BURGERS:
+            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            self.placement = Placement(self.n, n_sm, dev)
 
     def run(self, spec, n_steps, trace=None, steplog=None, vlog=None, inject_w=None, inject_u=None):
         """Advance all chains by n_steps in ONE launch of the fused kernel (ipmcmc_run).
@@ -193,6 +238,15 @@ class ChainBatch:
         b.vlog_dev = _ptr(vlog)
         b.inject_w_dev = _ptr(inject_w)
         b.inject_u_dev = _ptr(inject_u)
+        pl = self.placement
+        if pl is not None:
+            b.warps_per_cta = pl.W
+            if pl.active and self._work_prev is not None:
+                table = pl.update(self.counters[:, 2] - self._work_prev)
+                b.slot_chain_dev = _ptr(table)
+                b.n_slots = pl.n_slots
+            if pl.active:
+                self._work_prev = self.counters[:, 2].clone()
         check(lib.ipmcmc_run(self.problem.handle, C.byref(s), C.byref(b), self.n, int(n_steps), _stream()))
         self.step += int(n_steps)
         self.launches += 1
