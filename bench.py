@@ -91,7 +91,7 @@ def posterior_start(wl):
     return None
 
 
-def run_reference(args, wl, name):
+def run_reference(args, wl, name, out_fd):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -114,7 +114,7 @@ def run_reference(args, wl, name):
                 config=workload_config(wl, name, args),
                 cpu_baseline=dict(value=value, unit="chain-steps/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit="chain-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line, out_fd)
 
 
 def workload_config(wl, name, args):
@@ -203,7 +203,16 @@ def algorithmic_flops(wl, work_a, work_b):
     return 3444.0 * (work_a + work_b) + 48.0 * work_a
 
 
+def emit(line, out_fd):
+    os.write(out_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # Libraries (NCCL banner, torchrun notes) may write to stdout; the contract is ONE JSON line
+    # there.  Keep the real stdout for that line and point fd 1 at stderr for everything else.
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -223,7 +232,7 @@ def main():
     if args.mcmc_steps:
         wl["mcmc_steps"] = args.mcmc_steps
     if args.impl == "reference":
-        return run_reference(args, wl, args.workload)
+        return run_reference(args, wl, args.workload, out_fd)
 
     import torch
     import torch.distributed as dist
@@ -257,10 +266,11 @@ def main():
             chains.run(spec, S, trace=trace)
         torch.cuda.synchronize()
         c0 = chains.counters.sum(0).cpu().numpy()
+        sampler_clk = ClockSampler(local)                  # NVML init happens here, before the barrier
         if world > 1:
+            parallel.allreduce_pooled(chains.pooled(), 3)   # warm NCCL with the message of the final reduce
             dist.barrier()
         torch.cuda.synchronize()
-        sampler_clk = ClockSampler(local)
         sampler_clk.start()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K + 1)]
         launches0 = chains.launches
@@ -368,7 +378,7 @@ def main():
         line["cpu_baseline"] = dict(value=v, unit="chain-steps/s", cores=cores, kind="port",
                                     sample="%d processes x %d chain-steps of the same workload, NumPy restatement of "
                                            "the reference sampler (2 forward solves per step), %.1f s" % (cores, n, busy))
-    print(json.dumps(line), flush=True)
+    emit(line, out_fd)
     if world > 1:
         dist.destroy_process_group()
 

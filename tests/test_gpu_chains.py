@@ -193,3 +193,51 @@ def test_free_running_chain_statistics_vs_cpu_oracle(G):
     assert abs(acc_dev - np.mean(cpu_acc)) < 0.12
     # both samplers have left the prior-mean start in the same direction (towards delta_1 = u*_1)
     assert dev_post.mean(0)[0] < -0.3 and cpu.mean(0)[0] < -0.3
+
+
+def test_host_buffer_entry_point_matches_device_path(G):
+    """ipmcmc_sample_host (host pointers in/out, copies inside) == MCMCSampler.run on the same seed."""
+    import ctypes as C
+    import ip_mcmc_b200 as M
+    from ip_mcmc_b200 import _lib
+    f, pot, prior, _ = G.burgers_setup(32)
+    s = M.MCMCSampler(M.ConstSteppCNProposer(0.25, prior), M.CountedAccepter(M.pCNAccepter(pot)), np.random.default_rng(4))
+    n_chains, n = 9, 25
+    ref = s.run(np.zeros(3), n, 0, 1, n_chains=n_chains)
+    spec, _, _ = M.MCMCSampler(M.ConstSteppCNProposer(0.25, prior), M.CountedAccepter(M.pCNAccepter(pot)),
+                               np.random.default_rng(4))._compile(n, 0, 1, None)
+    assert spec.seed == s.last_run["seed"]
+
+    class FakeChains:       # c_desc only needs these attributes
+        _keep, chain_offset, step, problem = [], 0, 0, pot.problem()
+    desc = spec.c_desc(FakeChains, n)
+    u0 = np.zeros((n_chains, 3))
+    samples = np.empty((n_chains, n, 3))
+    counters = np.zeros((n_chains, 6), dtype=np.int64)
+    pooled = np.empty(2 * 3 + 7)
+    lib = _lib.load()
+    _lib.check(lib.ipmcmc_sample_host(pot.problem().handle, C.byref(desc), n_chains, n, _lib.as_double_p(u0), None,
+                                      _lib.as_double_p(samples), n, counters.ctypes.data_as(_lib.c_int64_p),
+                                      _lib.as_double_p(pooled), None))
+    assert np.array_equal(samples, ref)
+    assert counters[:, 0].sum() == n_chains * n and counters[:, 1].sum() == s.last_run["counters"]["accepts"]
+    assert pooled[0] == n_chains * n
+    np.testing.assert_allclose(pooled[1:4], ref.reshape(-1, 3).mean(0), rtol=1e-12)
+
+
+def test_placement_does_not_change_results(G):
+    """The work-aware slot table is pure scheduling: one-wave batches (placement active) give the
+    same chains as the same chains run inside a larger batch (placement inactive)."""
+    import ip_mcmc_b200 as M
+    import torch
+    f, pot, prior, _ = G.burgers_setup(32)
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    n = 5 * n_sm + 3                      # W = 6 warps per CTA -> placement active
+    mk = lambda: M.MCMCSampler(M.ConstSteppCNProposer(0.25, prior), M.pCNAccepter(pot), np.random.default_rng(8))
+    a = mk()
+    out_a = a.run(np.zeros(3), 12, 0, 1, n_chains=n, steps_per_launch=4)      # 3 launches: table used from the 2nd
+    assert a.last_run["chains"].placement.active
+    b = mk()
+    out_b = b.run(np.zeros(3), 12, 0, 1, n_chains=9 * n_sm)                   # > 8 n_SM: no placement
+    assert not b.last_run["chains"].placement.active
+    assert np.array_equal(out_a, out_b[:n])
