@@ -22,40 +22,37 @@ struct LorenzDev {
     PotentialDev pot;
 };
 
-// Dormand-Prince tableau (scipy rk.py RK45.A/B/C/E)
-#define DP_A21 (1.0 / 5)
-#define DP_A31 (3.0 / 40)
-#define DP_A32 (9.0 / 40)
-#define DP_A41 (44.0 / 45)
-#define DP_A42 (-56.0 / 15)
-#define DP_A43 (32.0 / 9)
-#define DP_A51 (19372.0 / 6561)
-#define DP_A52 (-25360.0 / 2187)
-#define DP_A53 (64448.0 / 6561)
-#define DP_A54 (-212.0 / 729)
-#define DP_A61 (9017.0 / 3168)
-#define DP_A62 (-355.0 / 33)
-#define DP_A63 (46732.0 / 5247)
-#define DP_A64 (49.0 / 176)
-#define DP_A65 (-5103.0 / 18656)
-#define DP_B1 (35.0 / 384)
-#define DP_B3 (500.0 / 1113)
-#define DP_B4 (125.0 / 192)
-#define DP_B5 (-2187.0 / 6784)
-#define DP_B6 (11.0 / 84)
-#define DP_E1 (-71.0 / 57600)
-#define DP_E3 (71.0 / 16695)
-#define DP_E4 (-71.0 / 1920)
-#define DP_E5 (17253.0 / 339200)
-#define DP_E6 (-22.0 / 525)
-#define DP_E7 (1.0 / 40)
+// Dormand-Prince tableau (scipy rk.py RK45.A/B/C/E) in constant memory: the FMAs take the
+// coefficient as a constant-bank operand (no UMOV pairs to materialise 64-bit immediates, and a
+// two-register DFMA issues every 2 cycles instead of 3).
+enum : int { A21, A31, A32, A41, A42, A43, A51, A52, A53, A54, A61, A62, A63, A64, A65,
+             B1, B3, B4, B5, B6, E1, E3, E4, E5, E6, E7, DP_N };
+__constant__ double DP[DP_N] = {
+    1.0 / 5, 3.0 / 40, 9.0 / 40, 44.0 / 45, -56.0 / 15, 32.0 / 9,
+    19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729,
+    9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656,
+    35.0 / 384, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84,
+    -71.0 / 57600, 71.0 / 16695, -71.0 / 1920, 17253.0 / 339200, -22.0 / 525, 1.0 / 40};
 #define RK_SAFETY 0.9
 #define RK_MIN_FACTOR 0.2
 #define RK_MAX_FACTOR 10.0
 
+// 1/x to ~1 ulp: MUFU.RCP64H seed + two Newton rounds (branch-free, unlike the IEEE division)
+__device__ __forceinline__ double rcp_newton(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+
 // Parameters of one chain's ODE, identical on all lanes of its group.
 struct LorenzTheta {
     double F, h, c, b;
+    double hc, hJ;  // h*c (lorenz.py:42) and h/J (lorenz.py:98), hoisted out of the RHS
+    __device__ __forceinline__ void finish(int J) {
+        hc = h * c;
+        hJ = h / (double)J;
+    }
 };
 
 template <int J>
@@ -76,11 +73,15 @@ struct LorenzLanes {
         src_p1 = base + (k + 1) % K_;
     }
 
-    // sum over the lanes of the group, same order on every lane (lane 0 first)
+    // sum over the K lanes of the group: shuffle-down tree into the group's first lane, then one
+    // broadcast, so every lane of the chain holds the SAME bits (control flow stays group-uniform)
     __device__ __forceinline__ double group_sum(double v) const {
-        double s = __shfl_sync(FULL, v, base);
-        for (int j = 1; j < K; ++j) s = s + __shfl_sync(FULL, v, base + j);
-        return s;
+        double s = v;
+        for (int off = 1; off < K; off *= 2) {
+            const double t = __shfl_down_sync(FULL, s, off);
+            if (k + off < K) s = s + t;
+        }
+        return __shfl_sync(FULL, s, base);
     }
 
     // d(state)/dt in the reference's rounding order (lorenz.py:73-101)
@@ -102,8 +103,8 @@ struct LorenzLanes {
             } else {
                 s = np_pairwise_sum([&](int j) { return y[1 + j]; }, 0, J);
             }
-            out = out - (th.h * th.c) * (s / (double)J);
-            const double hx = th.h / (double)J * X;
+            out = out - th.hc * (s / (double)J);
+            const double hx = th.hJ * X;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const double Yp1 = y[1 + (j + 1) % J], Yp2 = y[1 + (j + 2) % J], Ym1 = y[1 + (j + J - 1) % J];
@@ -131,35 +132,37 @@ struct LorenzLanes {
                                               double (&ynew)[NV], double (&k7)[NV]) const {
         double k2[NV], k3[NV], k4[NV], k5[NV], k6[NV], ys[NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) ys[i] = fma(DP_A21 * k1[i], h, y[i]);
+        for (int i = 0; i < NV; ++i) ys[i] = fma(DP[A21] * k1[i], h, y[i]);
         rhs(th, ys, k2);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) ys[i] = fma(fma(DP_A32, k2[i], DP_A31 * k1[i]), h, y[i]);
+        for (int i = 0; i < NV; ++i) ys[i] = fma(fma(DP[A32], k2[i], DP[A31] * k1[i]), h, y[i]);
         rhs(th, ys, k3);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) ys[i] = fma(fma(DP_A43, k3[i], fma(DP_A42, k2[i], DP_A41 * k1[i])), h, y[i]);
+        for (int i = 0; i < NV; ++i) ys[i] = fma(fma(DP[A43], k3[i], fma(DP[A42], k2[i], DP[A41] * k1[i])), h, y[i]);
         rhs(th, ys, k4);
 #pragma unroll
         for (int i = 0; i < NV; ++i)
-            ys[i] = fma(fma(DP_A54, k4[i], fma(DP_A53, k3[i], fma(DP_A52, k2[i], DP_A51 * k1[i]))), h, y[i]);
+            ys[i] = fma(fma(DP[A54], k4[i], fma(DP[A53], k3[i], fma(DP[A52], k2[i], DP[A51] * k1[i]))), h, y[i]);
         rhs(th, ys, k5);
 #pragma unroll
         for (int i = 0; i < NV; ++i)
-            ys[i] = fma(fma(DP_A65, k5[i], fma(DP_A64, k4[i], fma(DP_A63, k3[i], fma(DP_A62, k2[i], DP_A61 * k1[i])))),
+            ys[i] = fma(fma(DP[A65], k5[i],
+                            fma(DP[A64], k4[i], fma(DP[A63], k3[i], fma(DP[A62], k2[i], DP[A61] * k1[i])))),
                         h, y[i]);
         rhs(th, ys, k6);
 #pragma unroll
         for (int i = 0; i < NV; ++i)
-            ynew[i] = fma(h, fma(DP_B6, k6[i], fma(DP_B5, k5[i], fma(DP_B4, k4[i], fma(DP_B3, k3[i], DP_B1 * k1[i])))),
+            ynew[i] = fma(h, fma(DP[B6], k6[i], fma(DP[B5], k5[i], fma(DP[B4], k4[i], fma(DP[B3], k3[i], DP[B1] * k1[i])))),
                           y[i]);
         rhs(th, ynew, k7);
         double e[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            const double err =
-                fma(DP_E7, k7[i], fma(DP_E6, k6[i], fma(DP_E5, k5[i], fma(DP_E4, k4[i], fma(DP_E3, k3[i], DP_E1 * k1[i]))))) * h;
+            const double err = fma(DP[E7], k7[i],
+                                   fma(DP[E6], k6[i],
+                                       fma(DP[E5], k5[i], fma(DP[E4], k4[i], fma(DP[E3], k3[i], DP[E1] * k1[i]))))) * h;
             const double scale = fma(absmax_bits(y[i], ynew[i]), rtol, atol);
-            e[i] = err / scale;
+            e[i] = err * rcp_newton(scale);
         }
         return rms(e, inv_sqrt_n);
     }
@@ -240,7 +243,7 @@ struct LorenzSolve {
             const double err = L.attempt(th, y, f, h, P.rtol, P.atol, inv_sqrt_n, ynew, fnew);
             if (!done && !fail) {
                 if (err < 1.0) {
-                    double factor = (err == 0.0) ? RK_MAX_FACTOR : fmin(RK_MAX_FACTOR, RK_SAFETY * pow(err, -0.2));
+                    double factor = (err == 0.0) ? RK_MAX_FACTOR : fmin(RK_MAX_FACTOR, RK_SAFETY * exp(-0.2 * log(err)));
                     if (step_rejected) factor = fmin(1.0, factor);
                     h_abs = h_abs_used * factor;
                     t = t_new;
@@ -254,7 +257,7 @@ struct LorenzSolve {
                     new_step = true;
                     if (t == P.T) done = true;
                 } else {
-                    h_abs = h_abs_used * fmax(RK_MIN_FACTOR, RK_SAFETY * pow(err, -0.2));
+                    h_abs = h_abs_used * fmax(RK_MIN_FACTOR, RK_SAFETY * exp(-0.2 * log(err)));
                     step_rejected = true;
                     new_step = false;
                     ++n_rej;   // NaN error norms land here too, as in scipy (nan < 1 is False)

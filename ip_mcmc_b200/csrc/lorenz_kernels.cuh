@@ -29,7 +29,7 @@ __device__ __forceinline__ void lorenz_store_state(const LorenzLanes<J> &L, doub
 // for every chain of the warp at once.  `ui`: component i of the chain's u on group lane i.
 // S.y carries the initial condition in and the end state out (lorenz_mcmc.py:66).
 template <int J>
-__device__ __noinline__ double lorenz_phi(const LorenzLanes<J> &L, const LorenzDev &P, double ui, LorenzSolve<J> &S,
+__device__ __forceinline__ double lorenz_phi(const LorenzLanes<J> &L, const LorenzDev &P, double ui, LorenzSolve<J> &S,
                                           bool active, double *Gs, double *r2) {
     // F, h, b = prior_means + u   (lorenz_mcmc.py:64)
     const double pi = (L.k < 3) ? P.param_mean[L.k] + ui : 0.0;
@@ -38,6 +38,7 @@ __device__ __noinline__ double lorenz_phi(const LorenzLanes<J> &L, const LorenzD
     th.h = __shfl_sync(FULL, pi, L.base + 1);
     th.b = __shfl_sync(FULL, pi, L.base + 2);
     th.c = P.c;
+    th.finish(J);
     double ykeep[J + 1];
 #pragma unroll
     for (int i = 0; i < J + 1; ++i) ykeep[i] = S.y[i];
@@ -134,17 +135,21 @@ __global__ void __launch_bounds__(32) lorenz_chain_kernel(const __grid_constant_
             if (C.vlog && own) C.vlog[(c * n_steps + s) * d + L.k] = vi;
             const bool ok = active && (!Sd.has_constraint || constraint_ok(Sd, Gp, vi));
             // The reference evaluates Phi(u) and then Phi(v) every step, each solve starting where
-            // the previous one ended (accepter.py:121-122 + lorenz_mcmc.py:66).
+            // the previous one ended (accepter.py:121-122 + lorenz_mcmc.py:66).  One inlined call
+            // site serves both passes so the integrator state stays in registers.
             const bool need_u = ok && (Sd.recompute_phi_u || isnan(phi_u));
-            if (__any_sync(FULL, need_u)) {
-                const double ph = lorenz_phi<J>(L, P, ui, S, need_u, Gs, r2);
-                if (need_u) {
-                    phi_u = ph;
-                    cnt[CNT_WORK_A] += S.n_acc;
-                    cnt[CNT_WORK_B] += S.n_rej;
+            double ph_v = 0.0;
+            for (int pass = __any_sync(FULL, need_u) ? 0 : 1; pass < 2; ++pass) {
+                const bool act = pass ? ok : need_u;
+                const double ph = lorenz_phi<J>(L, P, pass ? vi : ui, S, act, Gs, r2);
+                if (act) {
+                    if (pass) ph_v = ph; else phi_u = ph;
+                    if (!pass) {
+                        cnt[CNT_WORK_A] += S.n_acc;
+                        cnt[CNT_WORK_B] += S.n_rej;
+                    }
                 }
             }
-            const double ph_v = lorenz_phi<J>(L, P, vi, S, ok, Gs, r2);
             bool accepted = false;
             double phi_v = nan(""), a = nan("");
             int work = 0;
@@ -220,11 +225,12 @@ __global__ void __launch_bounds__(32) lorenz_rhs_kernel(int K, long long n, cons
         double y[J + 1], dy[J + 1];
 #pragma unroll
         for (int i = 0; i < J + 1; ++i) y[i] = 0.0;
-        LorenzTheta th{0, 0, 0, 0};
+        LorenzTheta th{0, 0, 0, 0, 0, 0};
         if (active) {
             lorenz_load_state<J>(L, state + c * nvar, y);
-            th = LorenzTheta{theta[4 * c], theta[4 * c + 1], theta[4 * c + 2], theta[4 * c + 3]};
+            th = LorenzTheta{theta[4 * c], theta[4 * c + 1], theta[4 * c + 2], theta[4 * c + 3], 0, 0};
         }
+        th.finish(J);
         L.rhs(th, y, dy);
         if (active) lorenz_store_state<J>(L, out + c * nvar, dy);
     }
@@ -248,13 +254,14 @@ __global__ void __launch_bounds__(32) lorenz_attempt_kernel(int K, long long n, 
         double y[J + 1], f[J + 1], yn[J + 1], fn[J + 1];
 #pragma unroll
         for (int i = 0; i < J + 1; ++i) y[i] = 0.0;
-        LorenzTheta th{0, 0, 0, 0};
+        LorenzTheta th{0, 0, 0, 0, 0, 0};
         double h = 0.0;
         if (active) {
             lorenz_load_state<J>(L, state + c * nvar, y);
-            th = LorenzTheta{theta[4 * c], theta[4 * c + 1], theta[4 * c + 2], theta[4 * c + 3]};
+            th = LorenzTheta{theta[4 * c], theta[4 * c + 1], theta[4 * c + 2], theta[4 * c + 3], 0, 0};
             h = hstep[c];
         }
+        th.finish(J);
         L.rhs(th, y, f);
         const double err = L.attempt(th, y, f, h, rtol, atol, inv_sqrt_n, yn, fn);
         if (active) {

@@ -70,3 +70,26 @@ elif what == "occupancy":
         nfv = r["work"][:, 0].double().mean().item()
         print("wpc %d chains %5d (%.2f warps/SMSP): %.3f ms  -> %.0f cycles per FV step per warp-slot, TFLOP/s %.2f"
               % (wpc, nch, nch / 592.0, t, t * 1e-3 * 1.965e9 / nfv, 29.0 * N * nfv * nch / (t * 1e-3) / 1e12))
+elif what == "chainflat":
+    # chain kernel with IDENTICAL work on every chain (zero injected noise, never accept):
+    # separates per-step cost from load imbalance
+    from ip_mcmc_b200 import _lib
+    f = M.BurgersFVM(N=N, numerics=numerics)
+    y = f.at_parameters(TRUTH)
+    pot = M.EvolutionPotential(f, y, M.GaussianDistribution(np.zeros(5), 0.05 ** 2 * np.identity(5)))
+    S = 20
+    for nch in (592, 1024, 1036, 1184, 2368, 8192):
+        spec = M.SamplerSpec(3, _lib.PROPOSE_PCN, _lib.ACCEPT_PCN, coef_u=1.0, coef_w=0.0)
+        ch = M.ChainBatch(pot.problem(), TRUTH - PM, n_chains=nch)
+        w = torch.zeros((nch, S, 3), dtype=torch.float64, device="cuda")
+        U = torch.ones((nch, S), dtype=torch.float64, device="cuda")
+        ts = []
+        for _ in range(4):
+            c0 = ch.counters[:, 2].sum().item()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ch.run(spec, S, inject_w=w, inject_u=U); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+            nfv = (ch.counters[:, 2].sum().item() - c0) / nch
+        t = min(ts)
+        print("chains %5d W=%d (%.2f warps/SMSP): %.3f ms, %d FV steps/chain -> %.0f cycles per FV step per warp-slot, TFLOP/s %.2f"
+              % (nch, ch.placement.W, nch / 592.0, t, nfv, t * 1e-3 * 1.965e9 / nfv, 29.0 * N * nfv * nch / (t * 1e-3) / 1e12))

@@ -63,6 +63,10 @@ __global__ void thr(double *out, long long *cyc, double a, double b, int n) {
                 if (MIX == 5) { x[k] = fma(x[k], a, b); z = z * 3u + (uint32_t)k; }     // DFMA + 1 IMAD each
                 if (MIX == 6) { x[k] = fma(x[k], a, b); z = z * 3u + (uint32_t)k; z ^= z >> 3; }  // DFMA + 2-3 ALU each
                 if (MIX == 7) x[k] = fma(x[k], x[(k + 1) & 7], x[(k + 2) & 7]);         // DFMA, 3 distinct operands
+                if (MIX == 8) x[k] = fma(x[k], -0.5, x[(k + 1) & 7]);                   // DFMA imm, 2 distinct regs
+                if (MIX == 9) x[k] = x[k] * fabs(x[(k + 1) & 7]);                       // DMUL with |.|
+                if (MIX == 10) x[k] = (__double2hiint(x[(k + 1) & 7]) >= 0) ? x[k] + a : x[(k + 2) & 7];  // DADD + ISETP + 2 FSEL
+                if (MIX == 11) x[k] = fma(x[k], a, x[(k + 1) & 7]);                     // DFMA const-bank operand + 2 regs
             }
         }
     }
@@ -107,5 +111,9 @@ int main() {
     run_thr<5>("DFMA + 1 IMAD");
     run_thr<6>("DFMA + IMAD,SHF,LOP3");
     run_thr<7>("DFMA 3 distinct operands");
+    run_thr<8>("DFMA imm + 2 regs");
+    run_thr<9>("DMUL x*|y|");
+    run_thr<10>("DADD + ISETP + 2 FSEL");
+    run_thr<11>("DFMA const-bank + 2 regs");
     return 0;
 }
