@@ -11,7 +11,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libipmcmc.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "philox.cuh", "burgers.cuh", "burgers_kernels.cuh", "lorenz.cuh",
+HEADERS = ["common.cuh", "philox.cuh", "burgers.cuh", "burgers_kernels.cuh", "burgers_team.cuh", "lorenz.cuh",
            "lorenz_kernels.cuh", "sampler.cuh", os.path.join("..", "..", "include", "ipmcmc.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",
               "-std=c++17", "--extended-lambda", "--split-compile=0", "-shared", "-Xcompiler", "-fPIC"]

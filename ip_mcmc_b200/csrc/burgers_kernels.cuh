@@ -4,6 +4,7 @@
 // state is staged once per solve in shared memory for the windowed trapezoid measurement.
 #pragma once
 #include "burgers.cuh"
+#include "burgers_team.cuh"
 #include "sampler.cuh"
 
 namespace ipmcmc {
@@ -181,6 +182,164 @@ __global__ void __launch_bounds__(256) burgers_chain_kernel(const __grid_constan
             for (int k = 0; k < CNT_N; ++k) C.counters[c * CNT_N + k] += cnt[k];
         }
         __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// team kernels: one CTA of TM warps per chain (N = TM*32*CPL cells > 1024)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t burgers_team_smem_bytes(int N) {
+    return sizeof(TeamXch) + (size_t)(N + 2 * IPMCMC_MAX_OBS) * sizeof(double);
+}
+
+// Every warp of the team calls this with the same ui; warp 0 measures and evaluates Phi, the value is
+// broadcast through shared memory so that all warps take the same accept decision.
+template <int CPL, int NUMERICS, int TM>
+__device__ __noinline__ double burgers_team_phi(const BurgersDev &B, TeamXch &X, double ui, double *state, double *Gs,
+                                                double *r2, int tw, int lane, int &n_fv) {
+    const double pi = (lane < B.d) ? B.param_mean[lane] + ui : 0.0;
+    const double p0 = shfl(pi, 0), p1 = shfl(pi, 1), p2 = shfl(pi, 2);
+    BurgersTeam<CPL, NUMERICS, TM> W;
+    n_fv = W.integrate(B, X, p0, p1, p2, tw, lane);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) state[(tw * 32 + lane) * CPL + k] = W.u[k];
+    __syncthreads();
+    if (tw == 0) {
+        burgers_measure(B, state, Gs, lane);
+        const double phi = potential_from_G(B.pot, Gs, r2, lane, 32, FULL);
+        if (lane == 0) X.phi = W.capped ? nan("") : phi;
+    }
+    __syncthreads();
+    return X.phi;
+}
+
+template <int CPL, int NUMERICS, int TM>
+__global__ void __launch_bounds__(32 * TM) burgers_team_forward_kernel(const __grid_constant__ BurgersDev B, long long n,
+                                                                      const double *__restrict__ u,
+                                                                      double *__restrict__ G, double *__restrict__ phi,
+                                                                      double *__restrict__ state_out,
+                                                                      long long *__restrict__ work) {
+    extern __shared__ double smem_all[];
+    TeamXch &X = *reinterpret_cast<TeamXch *>(smem_all);
+    double *state = smem_all + sizeof(TeamXch) / sizeof(double), *Gs = state + B.N, *r2 = Gs + IPMCMC_MAX_OBS;
+    const int tw = threadIdx.x >> 5, lane = lane_id();
+    for (long long c = blockIdx.x; c < n; c += gridDim.x) {
+        const double ui = (lane < B.d) ? u[c * B.d + lane] : 0.0;
+        int n_fv;
+        const double ph = burgers_team_phi<CPL, NUMERICS, TM>(B, X, ui, state, Gs, r2, tw, lane, n_fv);
+        if (G && tw == 0)
+            for (int i = lane; i < B.pot.q; i += 32) G[c * B.pot.q + i] = Gs[i];
+        if (state_out)
+            for (int i = threadIdx.x; i < B.N; i += blockDim.x) state_out[c * B.N + i] = state[i];
+        if (threadIdx.x == 0) {
+            if (phi) phi[c] = ph;
+            if (work) {
+                work[2 * c] = n_fv;
+                work[2 * c + 1] = 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int CPL, int NUMERICS, int TM>
+__global__ void __launch_bounds__(32 * TM) burgers_team_chain_kernel(const __grid_constant__ BurgersDev B,
+                                                                    const __grid_constant__ SamplerDev S,
+                                                                    const __grid_constant__ ChainBufDev C,
+                                                                    long long n_chains, long long n_steps) {
+    extern __shared__ double smem_all[];
+    TeamXch &X = *reinterpret_cast<TeamXch *>(smem_all);
+    double *state = smem_all + sizeof(TeamXch) / sizeof(double), *Gs = state + B.N, *r2 = Gs + IPMCMC_MAX_OBS;
+    const int tw = threadIdx.x >> 5, lane = lane_id();
+    const bool writer = tw == 0;  // all warps run the same Metropolis logic; warp 0 owns the global writes
+    const Group Gp{0, 32, lane, FULL};
+    const int d = S.d;
+    for (long long c = blockIdx.x; c < n_chains; c += gridDim.x) {
+        const long long cg = S.chain_offset + c;
+        double ui = (lane < d) ? C.u[c * d + lane] : 0.0;
+        double phi_u = C.phi[c];
+        long long cnt[CNT_N];
+#pragma unroll
+        for (int k = 0; k < CNT_N; ++k) cnt[k] = 0;
+        int n_fv;
+        __syncthreads();  // everyone has read the chain state before warp 0 may overwrite it at the end
+        if (isnan(phi_u)) {
+            phi_u = burgers_team_phi<CPL, NUMERICS, TM>(B, X, ui, state, Gs, r2, tw, lane, n_fv);
+            cnt[CNT_WORK_A] += n_fv;
+            cnt[CNT_WORK_B] += 1;
+        }
+        double reg_u = (S.accepter == IPMCMC_ACCEPT_RW) ? prior_regulariser(S, Gp, ui) : 0.0;
+        Welford mom{C.mom_count[c], (lane < d) ? C.mom_mean[c * d + lane] : 0.0,
+                    (lane < d) ? C.mom_m2[c * d + lane] : 0.0};
+        long long n_rec = 0;
+        for (long long s = 0; s < n_steps; ++s) {
+            const long long gstep = S.first_step + s;
+            double ca, cb;
+            step_coefs(S, gstep, ca, cb);
+            const double w = proposal_noise(S, C, Gp, c, cg, s, n_steps, gstep);
+            const double vi = ca * ui + cb * w;
+            if (writer && C.vlog && lane < d) C.vlog[(c * n_steps + s) * d + lane] = vi;
+            bool accepted = false;
+            double phi_v = nan(""), a = nan("");
+            n_fv = 0;
+            const bool ok = !S.has_constraint || constraint_ok(S, Gp, vi);
+            if (ok) {
+                if (S.recompute_phi_u) {
+                    int nf0;
+                    phi_u = burgers_team_phi<CPL, NUMERICS, TM>(B, X, ui, state, Gs, r2, tw, lane, nf0);
+                    cnt[CNT_WORK_A] += nf0;
+                    cnt[CNT_WORK_B] += 1;
+                }
+                phi_v = burgers_team_phi<CPL, NUMERICS, TM>(B, X, vi, state, Gs, r2, tw, lane, n_fv);
+                cnt[CNT_WORK_A] += n_fv;
+                cnt[CNT_WORK_B] += 1;
+                double reg_v = 0.0;
+                if (S.accepter == IPMCMC_ACCEPT_RW) reg_v = prior_regulariser(S, Gp, vi);
+                a = exp((phi_u + reg_u) - (phi_v + reg_v));
+                const double U = C.inject_u ? C.inject_u[c * n_steps + s]
+                                            : draw_uniform(S.seed, (uint64_t)cg, (uint64_t)gstep);
+                accepted = a > U;
+                if (!isfinite(phi_v)) cnt[CNT_NONFINITE] += 1;
+                if (accepted) {
+                    ui = vi;
+                    phi_u = phi_v;
+                    reg_u = reg_v;
+                }
+            } else {
+                cnt[CNT_CONSTRAINT] += 1;
+            }
+            cnt[CNT_CALLS] += 1;
+            cnt[CNT_ACCEPTS] += accepted ? 1 : 0;
+            if (writer && C.steplog && lane == 0) {
+                double *L = C.steplog + (c * n_steps + s) * 4;
+                L[0] = phi_v;
+                L[1] = a;
+                L[2] = accepted ? 1.0 : 0.0;
+                L[3] = (double)n_fv;
+            }
+            if (S.record_interval > 0 && gstep >= S.record_start &&
+                ((gstep - S.record_start + 1) % S.record_interval) == 0) {
+                mom.add(ui);
+                if (writer && C.trace && n_rec < C.n_record && lane < d)
+                    C.trace[(c * C.n_record + n_rec) * d + lane] = ui;
+                ++n_rec;
+            }
+        }
+        __syncthreads();
+        if (writer) {
+            if (lane < d) {
+                C.u[c * d + lane] = ui;
+                C.mom_mean[c * d + lane] = mom.mean;
+                C.mom_m2[c * d + lane] = mom.m2;
+            }
+            if (lane == 0) {
+                C.phi[c] = phi_u;
+                C.mom_count[c] = mom.count;
+#pragma unroll
+                for (int k = 0; k < CNT_N; ++k) C.counters[c * CNT_N + k] += cnt[k];
+            }
+        }
+        __syncthreads();
     }
 }
 

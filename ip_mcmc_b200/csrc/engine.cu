@@ -107,7 +107,8 @@ static int pick_cpl(int N) {
 extern "C" int ipmcmc_burgers_create(const ipmcmc_burgers_desc *d, ipmcmc_problem **out) {
     if (!d || !out) return fail(IPMCMC_EINVAL, "NULL argument");
     if (d->n_cells < 2) return fail(IPMCMC_EINVAL, "n_cells=%d < 2", d->n_cells);
-    if (!pick_cpl(d->n_cells)) return fail(IPMCMC_EUNSUPPORTED, "n_cells=%d > 1024 (register-resident warp solver)", d->n_cells);
+    if (!pick_cpl(d->n_cells) && d->n_cells != 2048 && d->n_cells != 4096)
+        return fail(IPMCMC_EUNSUPPORTED, "n_cells=%d: grids above 1024 cells must be 2048 or 4096 (2 or 4 warps per chain)", d->n_cells);
     if (d->n_params != 3) return fail(IPMCMC_EUNSUPPORTED, "PerturbedRiemannIC takes 3 parameters, got %d", d->n_params);
     if (d->numerics != IPMCMC_NUMERICS_EXACT && d->numerics != IPMCMC_NUMERICS_FUSED) return fail(IPMCMC_EINVAL, "bad numerics");
     if (!d->x || !d->param_mean || !d->win_left || !d->win_right) return fail(IPMCMC_EINVAL, "NULL table");
@@ -202,6 +203,33 @@ static int burgers_launch_chain(ipmcmc_problem *p, const SamplerDev &S, const Ch
     return 0;
 }
 
+template <int NUM, int TM>
+static int burgers_launch_team_forward(ipmcmc_problem *p, long long n, const double *u, double *G, double *phi,
+                                       double *state, long long *work, cudaStream_t st) {
+    const size_t smem = burgers_team_smem_bytes(p->b.N);
+    auto kern = burgers_team_forward_kernel<32, NUM, TM>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid_for(n), 32 * TM, smem, st>>>(p->b, n, u, G, phi, state, work);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+template <int NUM, int TM>
+static int burgers_launch_team_chain(ipmcmc_problem *p, const SamplerDev &S, const ChainBufDev &C, long long n_chains,
+                                     long long n_steps, cudaStream_t st) {
+    const size_t smem = burgers_team_smem_bytes(p->b.N);
+    auto kern = burgers_team_chain_kernel<32, NUM, TM>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid_for(n_chains), 32 * TM, smem, st>>>(p->b, S, C, n_chains, n_steps);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+#define BURGERS_TEAM_DISPATCH(FN, ...)                                                                  \
+    do {                                                                                                \
+        const bool fused = p->numerics == IPMCMC_NUMERICS_FUSED;                                        \
+        if (p->b.N == 2048) return fused ? FN<NUM_FUSED, 2>(__VA_ARGS__) : FN<NUM_EXACT, 2>(__VA_ARGS__); \
+        if (p->b.N == 4096) return fused ? FN<NUM_FUSED, 4>(__VA_ARGS__) : FN<NUM_EXACT, 4>(__VA_ARGS__); \
+    } while (0)
+
 #define BURGERS_CASE(FN, C, ...)                                                                        \
     case C:                                                                                             \
         if (fused) return padded ? FN<C, NUM_FUSED, true>(__VA_ARGS__) : FN<C, NUM_FUSED, false>(__VA_ARGS__); \
@@ -242,6 +270,8 @@ extern "C" int ipmcmc_forward(ipmcmc_problem *p, int64_t n, const double *u_dev,
     if (n <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (p->model == IPMCMC_MODEL_BURGERS) {
+        if (p->b.N > 1024)
+            BURGERS_TEAM_DISPATCH(burgers_launch_team_forward, p, n, u_dev, G_dev, phi_dev, state_dev, (long long *)work_dev, st);
         BURGERS_DISPATCH(burgers_launch_forward, p, n, u_dev, G_dev, phi_dev, state_dev, (long long *)work_dev, st);
     }
     if (!state_dev) return fail(IPMCMC_EINVAL, "Lorenz forward needs state_dev (carried initial condition)");
@@ -335,6 +365,7 @@ extern "C" int ipmcmc_run(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, const
         int wpc = b->warps_per_cta > 0 ? b->warps_per_cta : 4;
         if (wpc > 8) return fail(IPMCMC_EINVAL, "warps_per_cta=%d > 8", wpc);
         if (b->slot_chain_dev && b->n_slots < 1) return fail(IPMCMC_EINVAL, "slot_chain_dev without n_slots");
+        if (p->b.N > 1024) BURGERS_TEAM_DISPATCH(burgers_launch_team_chain, p, S, C, n_chains, n_steps, st);
         BURGERS_DISPATCH(burgers_launch_chain, p, S, C, n_chains, n_steps, wpc, st);
     }
     const int groups = lorenz_groups(p->l.K);

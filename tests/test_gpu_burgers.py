@@ -122,3 +122,41 @@ def test_full_size_properties(G):
         const = 0.5 * (5 * np.log(2 * np.pi) + np.sum(np.log(np.full(5, 0.05 ** 2))))
         np.testing.assert_allclose(phi, const, rtol=1e-12)
         assert np.all(w[:, 0] == w[0, 0]) and abs(w[0, 0] - 1.027 * N) < 0.02 * N
+
+
+@pytest.mark.parametrize("N", [2048, 4096])
+def test_team_solver_large_grids_vs_oracle(G, N):
+    """Grids above 1024 cells run on 2 / 4 warps per chain (burgers_team.cuh): EXACT numerics stay
+    bit-identical to the oracle, FUSED within 1e-10; a short chain replays the oracle's decisions."""
+    import ip_mcmc_b200 as M
+    from ip_mcmc_b200 import _lib
+    rng = np.random.default_rng(N)
+    u = np.vstack([G.TRUTH - G.PRIOR_MEAN, 0.25 * rng.standard_normal((2, 3))])
+    P = B.BurgersProblem(N)
+    f, pot, prior, y = G.burgers_setup(N, "exact")
+    assert np.array_equal(y, P.G_params(G.TRUTH))
+    opot = O.Potential(P, y, G.NOISE_COV)
+    r = pot.problem().forward(u, want_state=True)
+    ref_phi = []
+    for i in range(len(u)):
+        end = P.end_state(P.prior_mean + u[i])
+        assert np.array_equal(r["state"][i].cpu().numpy(), end), (N, i)
+        assert r["work"][i, 0].item() == P.last_n_fv
+        assert np.array_equal(r["G"][i].cpu().numpy(), P.G(u[i]))
+        ref_phi.append(opot(u[i]))
+        assert r["phi"][i].item() == ref_phi[-1]
+    ff, fpot, _, _ = G.burgers_setup(N, "fused", y=y)
+    rf = fpot.problem().forward(u)
+    np.testing.assert_allclose(rf["phi"].cpu().numpy(), ref_phi, rtol=RTOL)
+    np.testing.assert_allclose(rf["G"].cpu().numpy(), r["G"].cpu().numpy(), rtol=RTOL, atol=1e-13)
+    # chain replay (pCN beta = 0.25) against the oracle with the same injected noise
+    n = 4
+    z = 0.25 * rng.standard_normal((n, 3))
+    U = rng.random(n)
+    start = G.TRUTH - G.PRIOR_MEAN
+    ref = O.run_chain(opot, start, z, U, O.PCN, O.PCN, 0.25)
+    spec = M.SamplerSpec(3, _lib.PROPOSE_PCN, _lib.ACCEPT_PCN, coef_u=np.sqrt(1 - 0.25 ** 2), coef_w=0.25)
+    states, slog, vlog, ch = G.run_injected(pot, spec, start, z, U, n_copies=3)
+    for c in range(3):
+        assert np.array_equal(states[c], ref["u"]) and np.array_equal(slog[c, :, 0], ref["phi_v"])
+    assert ch.counters[:, 1].tolist() == [ref["accepts"]] * 3
