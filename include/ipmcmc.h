@@ -84,7 +84,7 @@ typedef struct ipmcmc_burgers_desc {
     int32_t n_cells;          /* N interior cells (the solver carries N+2 with ghosts)          */
     int32_t numerics;         /* IPMCMC_NUMERICS_*                                              */
     int32_t max_fv_steps;     /* safety cap on FV time steps per solve (<=0: 64*N+1024)         */
-    int32_t n_params;         /* d = 3 (delta_1, delta_2, sigma)                                */
+    int32_t n_params;         /* d = 3 + n_kl_modes: (delta_1, delta_2, sigma, a_1..a_m)        */
     double T;                 /* end time (the last step is NOT clipped, rusanov.py:40-45)      */
     double dx;                /* solver spacing = linspace retstep (rusanov.py:22-25)           */
     double dx_meas;           /* Measurer spacing x[1]-x[0] (utilities.py:91)                   */
@@ -92,6 +92,12 @@ typedef struct ipmcmc_burgers_desc {
     const double *param_mean; /* host [d] prior mean added to u (utilities.py:41)               */
     const int32_t *win_left;  /* host [q] searchsorted limits into the interior array           */
     const int32_t *win_right; /* host [q]                                                       */
+    /* Extension (not in the reference; BASELINE.json north_star "truncated KL/spectral prior"):
+       w0(x) = PerturbedRiemannIC(x) + sum_k a_k * phi_k(x), the coefficients a_k being parameters
+       3..3+m-1 with a diagonal (KL) prior.  kl_basis is phi_k at the N+2 cell centres.          */
+    int32_t n_kl_modes;       /* m (0 = the reference's 3-parameter problem)                    */
+    int32_t reserved;
+    const double *kl_basis;   /* host [m * (N+2)], row-major (mode, cell); NULL when m = 0      */
     ipmcmc_potential_desc potential;
 } ipmcmc_burgers_desc;
 

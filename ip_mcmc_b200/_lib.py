@@ -27,7 +27,8 @@ class BurgersDesc(C.Structure):
     _fields_ = [("n_cells", C.c_int32), ("numerics", C.c_int32), ("max_fv_steps", C.c_int32),
                 ("n_params", C.c_int32), ("T", C.c_double), ("dx", C.c_double), ("dx_meas", C.c_double),
                 ("x", c_double_p), ("param_mean", c_double_p), ("win_left", c_int32_p),
-                ("win_right", c_int32_p), ("potential", PotentialDesc)]
+                ("win_right", c_int32_p), ("n_kl_modes", C.c_int32), ("reserved", C.c_int32),
+                ("kl_basis", c_double_p), ("potential", PotentialDesc)]
 
 
 class LorenzDesc(C.Structure):

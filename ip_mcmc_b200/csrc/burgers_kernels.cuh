@@ -37,9 +37,8 @@ __device__ __noinline__ double burgers_phi(const BurgersDev &B, double ui, doubl
                                               int lane, int &n_fv) {
     // FVMObservationOperator.__call__ (utilities.py:40-41): IC(u_0 + u)
     const double pi = (lane < B.d) ? B.param_mean[lane] + ui : 0.0;
-    const double p0 = shfl(pi, 0), p1 = shfl(pi, 1), p2 = shfl(pi, 2);
     BurgersWarp<CPL, NUMERICS, PADDED> W;
-    n_fv = W.integrate(B, p0, p1, p2, lane);
+    n_fv = W.integrate(B, pi, lane);
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
         const int c = lane * CPL + k;
@@ -198,9 +197,8 @@ template <int CPL, int NUMERICS, int TM>
 __device__ __noinline__ double burgers_team_phi(const BurgersDev &B, TeamXch &X, double ui, double *state, double *Gs,
                                                 double *r2, int tw, int lane, int &n_fv) {
     const double pi = (lane < B.d) ? B.param_mean[lane] + ui : 0.0;
-    const double p0 = shfl(pi, 0), p1 = shfl(pi, 1), p2 = shfl(pi, 2);
     BurgersTeam<CPL, NUMERICS, TM> W;
-    n_fv = W.integrate(B, X, p0, p1, p2, tw, lane);
+    n_fv = W.integrate(B, X, pi, tw, lane);
 #pragma unroll
     for (int k = 0; k < CPL; ++k) state[(tw * 32 + lane) * CPL + k] = W.u[k];
     __syncthreads();

@@ -176,9 +176,9 @@ struct BurgersTeam {
         return n;
     }
 
-    __device__ __forceinline__ int integrate(const BurgersDev &B, TeamXch &X, double p_left, double p_right,
-                                             double p_jump, int tw, int lane) {
+    __device__ __forceinline__ int integrate(const BurgersDev &B, TeamXch &X, double pi, int tw, int lane) {
         const int N = B.N;
+        const double p_left = shfl(pi, 0), p_right = shfl(pi, 1), p_jump = shfl(pi, 2);
         const double left = 1.0 + p_left;
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
@@ -187,6 +187,14 @@ struct BurgersTeam {
         }
         gL = (B.x[0] < p_jump) ? left : p_right;
         gR = (B.x[N + 1] < p_jump) ? left : p_right;
+        for (int m = 0; m < B.n_modes; ++m) {
+            const double a = shfl(pi, 3 + m);
+            const double *phi = B.basis + (size_t)m * (N + 2);
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) u[k] = u[k] + a * phi[(tw * 32 + lane) * CPL + k + 1];
+            gL = gL + a * phi[0];
+            gR = gR + a * phi[N + 1];
+        }
         BurgersConsts C;
         C.T = B.T;
         C.half_dx = B.half_dx;

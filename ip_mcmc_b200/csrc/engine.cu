@@ -109,7 +109,9 @@ extern "C" int ipmcmc_burgers_create(const ipmcmc_burgers_desc *d, ipmcmc_proble
     if (d->n_cells < 2) return fail(IPMCMC_EINVAL, "n_cells=%d < 2", d->n_cells);
     if (!pick_cpl(d->n_cells) && d->n_cells != 2048 && d->n_cells != 4096)
         return fail(IPMCMC_EUNSUPPORTED, "n_cells=%d: grids above 1024 cells must be 2048 or 4096 (2 or 4 warps per chain)", d->n_cells);
-    if (d->n_params != 3) return fail(IPMCMC_EUNSUPPORTED, "PerturbedRiemannIC takes 3 parameters, got %d", d->n_params);
+    if (d->n_kl_modes < 0 || d->n_kl_modes > IPMCMC_MAX_DIM - 3) return fail(IPMCMC_EUNSUPPORTED, "n_kl_modes=%d outside [0,%d]", d->n_kl_modes, IPMCMC_MAX_DIM - 3);
+    if (d->n_params != 3 + d->n_kl_modes) return fail(IPMCMC_EINVAL, "n_params=%d, expected 3 + n_kl_modes = %d", d->n_params, 3 + d->n_kl_modes);
+    if (d->n_kl_modes > 0 && !d->kl_basis) return fail(IPMCMC_EINVAL, "kl_basis is NULL");
     if (d->numerics != IPMCMC_NUMERICS_EXACT && d->numerics != IPMCMC_NUMERICS_FUSED) return fail(IPMCMC_EINVAL, "bad numerics");
     if (!d->x || !d->param_mean || !d->win_left || !d->win_right) return fail(IPMCMC_EINVAL, "NULL table");
     if (!(d->dx > 0)) return fail(IPMCMC_EINVAL, "dx must be > 0");
@@ -141,6 +143,12 @@ extern "C" int ipmcmc_burgers_create(const ipmcmc_burgers_desc *d, ipmcmc_proble
     rc = upload(p, d->x, sizeof(double) * (b.N + 2), &dev);
     if (rc) { ipmcmc_destroy(p); return rc; }
     b.x = (const double *)dev;
+    b.n_modes = d->n_kl_modes;
+    if (b.n_modes > 0) {
+        rc = upload(p, d->kl_basis, sizeof(double) * (size_t)b.n_modes * (b.N + 2), &dev);
+        if (rc) { ipmcmc_destroy(p); return rc; }
+        b.basis = (const double *)dev;
+    }
     rc = finish_create(p, out);
     if (rc) ipmcmc_destroy(p);
     return rc;

@@ -278,8 +278,10 @@ class SamplerSpec:
         self.factor_kind = 0
         if factor is not None:
             f = np.asarray(factor, dtype=np.float64)
-            if f.ndim == 2 and np.all(f == np.diag(np.diag(f))):
-                f = np.diag(f).copy()
+            if f.ndim == 2 and np.all((f != 0).sum(axis=1) == 1) and np.all((f != 0).sum(axis=0) == 1):
+                # diagonal covariance: numpy's SVD factor is a scaled signed permutation of z.  The z_i
+                # are iid Philox normals, so w_i = f_i * z_i has the same law without the permutation.
+                f = f[np.arange(f.shape[0]), np.argmax(f != 0, axis=1)].copy()
             if f.ndim == 1 and np.all(f == 1.0):
                 self.factor_kind = 0
             else:

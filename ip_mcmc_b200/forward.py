@@ -44,15 +44,21 @@ class BurgersFVM(ForwardModel):
     (FMA-contracted update, ~1e-13 relative agreement, fewer fp64 instructions).
     """
     kind = _lib.MODEL_BURGERS
-    n_params = 3
 
     def __init__(self, domain=(-1, 1), N=200, T=1, prior_means=(1.5, 0.25, -0.5),
-                 points=(-0.5, -0.25, 0.25, 0.5, 0.75), interval=0.1, numerics="exact", max_fv_steps=0):
+                 points=(-0.5, -0.25, 0.25, 0.5, 0.75), interval=0.1, numerics="exact", max_fv_steps=0,
+                 kl_modes=0):
         self.domain = (float(domain[0]), float(domain[1]))
         self.N = int(N)
         self.T = float(T)
-        self.prior_means = np.ascontiguousarray(prior_means, dtype=np.float64)
-        assert self.prior_means.shape == (3,), "PerturbedRiemannIC takes (delta_1, delta_2, sigma)"
+        self.kl_modes = int(kl_modes)
+        self.n_params = 3 + self.kl_modes
+        pm = np.asarray(prior_means, dtype=np.float64)
+        if pm.shape == (3,) and self.kl_modes:
+            pm = np.concatenate([pm, np.zeros(self.kl_modes)])      # KL coefficients are centred
+        self.prior_means = np.ascontiguousarray(pm)
+        assert self.prior_means.shape == (self.n_params,), \
+            "PerturbedRiemannIC takes (delta_1, delta_2, sigma) [+ kl_modes coefficients]"
         self.points = np.asarray(points, dtype=np.float64)
         self.interval = float(interval)
         if numerics not in ("exact", "fused"):
@@ -68,13 +74,31 @@ class BurgersFVM(ForwardModel):
         self.left_limits = np.searchsorted(xv, self.points - self.interval / 2, side="left").astype(np.int32)
         self.right_limits = np.searchsorted(xv, self.points + self.interval / 2, side="left").astype(np.int32)
         self.n_obs = self.points.shape[0]
+        # KL / spectral extension (north star): w0(x) = Riemann(x) + sum_k a_k sin(k pi (x-a)/(b-a)),
+        # k = 1..kl_modes, sampled at the N+2 cell centres like the reference samples its IC (rusanov.py:32)
+        self.kl_basis = self.sine_basis(self.x, self.domain, self.kl_modes)
+
+    @staticmethod
+    def sine_basis(x, domain, m):
+        a, b = domain
+        k = np.arange(1, m + 1, dtype=np.float64)[:, None]
+        return np.ascontiguousarray(np.sin(k * np.pi * (np.asarray(x)[None, :] - a) / (b - a)))
+
+    @staticmethod
+    def kl_prior_variances(m, scale=0.1, decay=2.0):
+        """lambda_k = scale^2 * k^-decay: a power-law KL spectrum for the coefficients a_k."""
+        return scale ** 2 * np.arange(1, m + 1, dtype=np.float64) ** (-decay)
 
     def _c_desc(self, keep):
         d = _lib.BurgersDesc()
         d.n_cells = self.N
         d.numerics = _lib.NUMERICS_FUSED if self.numerics == "fused" else _lib.NUMERICS_EXACT
         d.max_fv_steps = self.max_fv_steps
-        d.n_params = 3
+        d.n_params = self.n_params
+        d.n_kl_modes = self.kl_modes
+        if self.kl_modes:
+            d.kl_basis = _lib.as_double_p(self.kl_basis)
+            keep.append(self.kl_basis)
         d.T, d.dx, d.dx_meas = self.T, float(self.dx), float(self.dx_meas)
         d.x = _lib.as_double_p(self.x)
         d.param_mean = _lib.as_double_p(self.prior_means)
@@ -85,7 +109,7 @@ class BurgersFVM(ForwardModel):
 
     def __call__(self, u):
         """G(u) for one parameter vector (utilities.py:40-41) -> ndarray[q]."""
-        return self._problem().forward(np.asarray(u, dtype=np.float64).reshape(1, 3))["G"][0].cpu().numpy()
+        return self._problem().forward(np.asarray(u, dtype=np.float64).reshape(1, self.n_params))["G"][0].cpu().numpy()
 
     def batch(self, u, want_state=False):
         """G for [n, 3] parameter vectors; dict(G, work=(FV steps, 0), state=end states)."""
@@ -96,8 +120,8 @@ class BurgersFVM(ForwardModel):
         reference generates its noise-free data, burgers_mcmc.py:104,116 (prior mean + (params -
         prior mean) would round differently)."""
         if getattr(self, "_abs_model", None) is None:
-            self._abs_model = BurgersFVM(self.domain, self.N, self.T, np.zeros(3), self.points, self.interval,
-                                         self.numerics, self.max_fv_steps)
+            self._abs_model = BurgersFVM(self.domain, self.N, self.T, np.zeros(self.n_params), self.points,
+                                         self.interval, self.numerics, self.max_fv_steps, self.kl_modes)
         return self._abs_model(params)
 
 

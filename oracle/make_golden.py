@@ -275,7 +275,49 @@ def gen_lorenz(ref):
         record_chain(ref, fac, np.array([-1.9, 1.9, 0.9]), n, name, dict(T=T, beta=0.5, seed=1))
 
 
-GROUPS = dict(burgers=gen_burgers_forward, chains=gen_burgers_chains, kats=gen_operator_kats,
+def gen_burgers_kl(ref):
+    """EXTENSION fixture: the reference's RusanovFVM / Measurer / EvolutionPotential driven by an
+    initial condition of the form Riemann(x) + sum_k a_k phi_k(x) (the IC callable below is ours,
+    everything downstream of it is reference code)."""
+    U = ref.utilities
+    rng = np.random.default_rng(99)
+    for N, m in ((64, 4), (128, 8)):
+        integ = U.RusanovMCMC(U.BurgersEquation.flux, U.BurgersEquation.flux_prime, (-1, 1), N, 1)
+        x = integ.FVM.x
+        meas = U.Measurer(POINTS, INTERVAL, x[1:-1])
+        k = np.arange(1, m + 1, dtype=np.float64)[:, None]
+        basis = np.sin(k * np.pi * (x[None, :] - (-1)) / 2)
+        index = {float(xv): i for i, xv in enumerate(x)}
+
+        class RiemannKLIC:
+            def __init__(self, params):
+                self.base = U.PerturbedRiemannIC(params[:3])
+                self.a = params[3:]
+
+            def __call__(self, xv):
+                val = self.base(xv)
+                i = index[float(xv)]
+                for kk in range(m):
+                    val = val + self.a[kk] * basis[kk, i]
+                return val
+
+        mean = np.concatenate([PRIOR_MEAN, np.zeros(m)])
+        truth = np.concatenate([TRUTH, 0.05 * rng.standard_normal(m) / np.arange(1, m + 1)])
+        y = meas(integ(RiemannKLIC(truth)))
+        noise = ref.ip_mcmc.GaussianDistribution(np.zeros(5), NOISE_STD ** 2 * np.identity(5))
+        op = U.FVMObservationOperator(RiemannKLIC, mean, integ, meas)
+        pot = ref.ip_mcmc.EvolutionPotential(op, y, noise)
+        us = np.zeros((4, 3 + m))
+        us[1] = truth - mean
+        us[2:, :3] = PRIOR_STD * rng.standard_normal((2, 3))
+        us[2:, 3:] = 0.1 * rng.standard_normal((2, m)) / np.arange(1, m + 1)
+        ends = [integ(RiemannKLIC(mean + u)) for u in us]
+        np.savez(os.path.join(OUT, f"burgers_kl_N{N}_m{m}.npz"), N=N, m=m, u=us, truth=truth, y=y, basis=basis,
+                 end_state=np.array(ends), G=np.array([op(u) for u in us]), phi=np.array([pot(u) for u in us]))
+        print("burgers_kl", N, m)
+
+
+GROUPS = dict(burgers=gen_burgers_forward, kl=gen_burgers_kl, chains=gen_burgers_chains, kats=gen_operator_kats,
               lorenz=gen_lorenz)
 
 if __name__ == "__main__":

@@ -160,3 +160,46 @@ def test_team_solver_large_grids_vs_oracle(G, N):
     for c in range(3):
         assert np.array_equal(states[c], ref["u"]) and np.array_equal(slog[c, :, 0], ref["phi_v"])
     assert ch.counters[:, 1].tolist() == [ref["accepts"]] * 3
+
+
+@pytest.mark.parametrize("N,m", [(64, 4), (128, 8)])
+def test_kl_spectral_extension(G, N, m):
+    """North-star item (1): proposals xi from a truncated KL (diagonal, power-law) prior and an
+    initial condition carrying the KL modes.  Forward parity against the fixture produced with the
+    reference's solver; a pCN chain with d = 3 + m replays the oracle's decisions bit for bit."""
+    import ip_mcmc_b200 as M
+    from ip_mcmc_b200 import _lib
+    g = golden(f"burgers_kl_N{N}_m{m}.npz")
+    f = M.BurgersFVM(N=N, kl_modes=m)
+    assert np.array_equal(f.kl_basis, g["basis"]) and f.n_params == 3 + m
+    noise = M.GaussianDistribution(np.zeros(5), G.NOISE_COV)
+    pot = M.EvolutionPotential(f, g["y"], noise)
+    r = pot.problem().forward(g["u"], want_state=True)
+    assert np.array_equal(r["state"].cpu().numpy(), g["end_state"])
+    assert np.array_equal(r["G"].cpu().numpy(), g["G"]) and np.array_equal(r["phi"].cpu().numpy(), g["phi"])
+    assert np.array_equal(f.at_parameters(g["truth"]), g["y"])
+    ff = M.BurgersFVM(N=N, kl_modes=m, numerics="fused")
+    rf = M.EvolutionPotential(ff, g["y"], noise).problem().forward(g["u"])
+    np.testing.assert_allclose(rf["phi"].cpu().numpy(), g["phi"], rtol=RTOL)
+    # chain: prior = diag(0.25^2 x3, lambda_k) -> diagonal sample factor sqrt(lambda)
+    lam = np.concatenate([np.full(3, 0.25 ** 2), M.BurgersFVM.kl_prior_variances(m)])
+    prior = M.GaussianDistribution(f.prior_means, np.diag(lam))
+    beta, n = 0.2, 25
+    rng = np.random.default_rng(m)
+    w = rng.standard_normal((n, 3 + m)) * np.sqrt(lam)
+    U = rng.random(n)
+    P = B.BurgersProblem(N, kl_basis=g["basis"])
+    ref = O.run_chain(O.Potential(P, g["y"], G.NOISE_COV), np.zeros(3 + m), w, U, O.PCN, O.PCN, beta)
+    spec = M.SamplerSpec(3 + m, _lib.PROPOSE_PCN, _lib.ACCEPT_PCN, coef_u=np.sqrt(1 - beta ** 2), coef_w=beta)
+    states, slog, vlog, ch = G.run_injected(pot, spec, np.zeros(3 + m), w, U, n_copies=2)
+    assert np.array_equal(states[0], ref["u"]) and np.array_equal(states[1], ref["u"])
+    assert np.array_equal(slog[0, :, 0], ref["phi_v"]) and ref["accepts"] > 0
+    # free-running through the public API: Philox z scaled by sqrt(lambda) on the device
+    s = M.MCMCSampler(M.ConstSteppCNProposer(beta, prior), M.CountedAccepter(M.pCNAccepter(pot)), np.random.default_rng(3))
+    out = s.run(np.zeros(3 + m), 200, 0, 1, n_chains=64)
+    assert out.shape == (64, 200, 3 + m) and 0.02 < s.accepter.ratio() < 0.95
+    spec2, _, _ = s._compile(1, 0, 1, None)
+    assert spec2.factor_kind == 1 and np.allclose(np.abs(spec2.factor), np.sqrt(lam))
+    # the high modes are weakly informed: their posterior spread stays within the prior's
+    post_sd = out[:, 100:, 3:].reshape(-1, m).std(0)
+    assert np.all(post_sd < 1.5 * np.sqrt(lam[3:]))

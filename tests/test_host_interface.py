@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_struct_layout_matches_header_sizes():
     # field order and 8-byte alignment as declared in include/ipmcmc.h
     assert ctypes.sizeof(_lib.PotentialDesc) == 48
-    assert ctypes.sizeof(_lib.BurgersDesc) == 16 + 24 + 32 + 48
+    assert ctypes.sizeof(_lib.BurgersDesc) == 16 + 24 + 32 + 16 + 48
     assert ctypes.sizeof(_lib.LorenzDesc) == 16 + 32 + 8 + 48
     assert ctypes.sizeof(_lib.SamplerDesc) == 32 + 16 + 16 + 40 + 40
     assert ctypes.sizeof(_lib.ChainBuffers) == 15 * 8

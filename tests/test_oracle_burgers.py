@@ -102,3 +102,16 @@ def test_max_steps_cap_and_degenerate_state():
     # all-zero state: dt = inf, loop ends after one step with a NaN state (0*inf)
     u, t, n = B.rusanov_integrate(np.zeros(10), 0.1, 1)
     assert n == 1 and np.isinf(t)
+
+
+@pytest.mark.parametrize("N,m", [(64, 4), (128, 8)])
+def test_kl_extension_against_reference_solver_fixture(N, m):
+    """KL/spectral extension: IC = Riemann + sum_k a_k sin(k pi (x-a)/(b-a)).  The fixture was produced
+    by the reference's RusanovFVM / Measurer / EvolutionPotential driven by such an IC callable."""
+    g = golden(f"burgers_kl_N{N}_m{m}.npz")
+    P = B.BurgersProblem(N, kl_basis=g["basis"])
+    pot = M.Potential(P, g["y"], 0.05 ** 2 * np.identity(5))
+    for i, u in enumerate(g["u"]):
+        assert np.array_equal(P.end_state(P.prior_mean + u), g["end_state"][i])
+        assert np.array_equal(P.G(u), g["G"][i]) and pot(u) == g["phi"][i]
+    assert np.array_equal(P.G_params(g["truth"]), g["y"])
