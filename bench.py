@@ -355,8 +355,13 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]["traffic"]
+    except Exception:
+        pass
     roofline = dict(bound="fp64", achieved=res["achieved"], peak=peak, unit="TFLOP/s", frac=res["achieved"] / peak,
-                    traffic=None,
+                    traffic=traffic,
                     peak_source="DFMA micro-benchmark (ipmcmc_fp64_peak) measured in this run; MEASURED_PEAKS.json has "
                                 "no fp64 entry (nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
                     flops_model="29 FLOP per cell per SSPRK2 step x device-counted FV steps" if wl["model"] == "burgers"

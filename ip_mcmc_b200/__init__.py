@@ -12,7 +12,7 @@ from .potential import EvolutionPotential
 from .distribution import GaussianDistribution
 from .forward import BurgersFVM, Lorenz96Moments
 from .engine import Problem, ChainBatch, SamplerSpec, fp64_peak_tflops
-from . import stats, parallel
+from . import stats, parallel, studies
 
 # the stale name the reference's scripts import (lorenz_mcmc.py:6-10, burgers_mcmc.py:4-8)
 pCNProposer = ConstSteppCNProposer
@@ -20,4 +20,4 @@ pCNProposer = ConstSteppCNProposer
 __all__ = ["MCMCSampler", "ConstStepStandardRWProposer", "VarStepStandardRWProposer", "ConstSteppCNProposer",
            "VarSteppCNProposer", "pCNProposer", "StandardRWAccepter", "pCNAccepter", "CountedAccepter",
            "ConstrainAccepter", "BoxConstraint", "EvolutionPotential", "GaussianDistribution", "BurgersFVM",
-           "Lorenz96Moments", "Problem", "ChainBatch", "SamplerSpec", "fp64_peak_tflops", "stats", "parallel"]
+           "Lorenz96Moments", "Problem", "ChainBatch", "SamplerSpec", "fp64_peak_tflops", "stats", "parallel", "studies"]

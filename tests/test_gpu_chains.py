@@ -241,3 +241,14 @@ def test_placement_does_not_change_results(G):
     out_b = b.run(np.zeros(3), 12, 0, 1, n_chains=9 * n_sm)                   # > 8 n_SM: no placement
     assert not b.last_run["chains"].placement.active
     assert np.array_equal(out_a, out_b[:n])
+
+
+def test_grid_refinement_study_driver(G):
+    """Engine-side half of burgers_wasserstein_grid.py: VarStep RW + box-constrained accepter on
+    several grids, 3-D histograms on the device."""
+    from ip_mcmc_b200 import studies
+    out = studies.grid_refinement_study(grids=(32, 64), n_steps=300, n_chains=32, burn_in=100)
+    for N in (32, 64):
+        h = out[N]["histogram"]
+        assert h.shape == (20, 20, 20) and abs(h.sum() * 0.05 ** 3 - 1) < 1e-9
+        assert 0.01 < out[N]["acceptance"] < 0.99

@@ -223,3 +223,22 @@ def test_stats_autocorr_and_ess():
     assert 14 < tau < 25                                                            # (1+rho)/(1-rho) = 19
     n, mean, m2 = M.stats.merge_moments([(len(a), a.mean(0), ((a - a.mean(0)) ** 2).sum(0)) for a in np.split(x[:4998].reshape(-1, 1), 3)])
     assert n == 4998 and np.allclose(mean, x[:4998].mean()) and np.allclose(m2 / (n - 1), x[:4998].var(ddof=1))
+
+
+def test_studies_histogram_cache_and_schedule(tmp_path):
+    from ip_mcmc_b200 import studies
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((5000, 3)) * 0.3
+    x[0] = [0.5, 0.5, 0.5]                      # upper edge belongs to the last bin
+    iv = [(-0.5, 0.5)] * 3
+    h = studies.histogram3d(x, iv, bins=20).numpy()
+    ref, _ = np.histogramdd(x, bins=20, range=iv, density=True)
+    np.testing.assert_allclose(h, ref, rtol=1e-12)
+    calls = []
+    f = lambda a, b: calls.append(1) or np.arange(a * b, dtype=float).reshape(a, b)
+    r1 = studies.load_or_compute("chain", f, (3, 2), data_dir=str(tmp_path))
+    r2 = studies.load_or_compute("chain", f, (3, 2), data_dir=str(tmp_path))
+    assert len(calls) == 1 and np.array_equal(r1, r2) and (tmp_path / "chain.npy").exists()
+    g = golden("chain_burgers_varstep_rw_N64.npz")          # the reference's PWLinear(0.1, 0.001, 50)
+    s = studies.PWLinear(0.1, 0.001, 50)
+    assert np.array_equal([s(i) for i in range(1, 101)], g["schedule"]) and repr(s) == "pwl_0.1_0.001_50"
