@@ -67,6 +67,9 @@ __global__ void thr(double *out, long long *cyc, double a, double b, int n) {
                 if (MIX == 9) x[k] = x[k] * fabs(x[(k + 1) & 7]);                       // DMUL with |.|
                 if (MIX == 10) x[k] = (__double2hiint(x[(k + 1) & 7]) >= 0) ? x[k] + a : x[(k + 2) & 7];  // DADD + ISETP + 2 FSEL
                 if (MIX == 11) x[k] = fma(x[k], a, x[(k + 1) & 7]);                     // DFMA const-bank operand + 2 regs
+                if (MIX == 12) { double t = x[k] + a; t = t + b; x[k] = (__double2hiint(x[(k + 1) & 7]) >= 0) ? t + a : x[(k + 2) & 7]; }  // 3 DADD + ISETP + 2 FSEL
+                if (MIX == 13) { double t = x[k] + a; t = t + b; t = t * a; x[k] = (__double2hiint(x[(k + 1) & 7]) >= 0) ? t + a : x[(k + 2) & 7]; }  // 4 fp64 + 3 ALU
+                if (MIX == 14) { double t = x[k] + a; t = t + b; t = t * a; t = t + b; t = t * a; x[k] = (__double2hiint(x[(k + 1) & 7]) >= 0) ? t + a : x[(k + 2) & 7]; }  // 6 fp64 + 3 ALU
             }
         }
     }
@@ -115,5 +118,8 @@ int main() {
     run_thr<9>("DMUL x*|y|");
     run_thr<10>("DADD + ISETP + 2 FSEL");
     run_thr<11>("DFMA const-bank + 2 regs");
+    run_thr<12>("3 fp64 + 3 ALU (per group)");
+    run_thr<13>("4 fp64 + 3 ALU (per group)");
+    run_thr<14>("6 fp64 + 3 ALU (per group)");
     return 0;
 }
