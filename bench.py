@@ -124,7 +124,7 @@ def workload_config(wl, name, args):
                    noise_std=0.05, numerics=args.numerics)
     else:
         cfg.update(K=6, J=4, T=wl["T"], proposer="RW", delta=wl["delta"], solves_per_step=2,
-                   rtol=1e-3, atol=1e-6)
+                   rtol=1e-3, atol=1e-6, numerics=args.numerics)
     cfg["untimed_burn_in_steps"] = args.burn_in if wl["model"] == "burgers" else 0
     cfg["l2"] = "flushed between timed launches (256 MiB memset, untimed); working set << L2 anyway"
     cfg["parallelism"] = "chains sharded by global id, dp%d" % args.gpus
@@ -138,13 +138,16 @@ class ClockSampler(threading.Thread):
     BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
     NOTE = {"sw_power_cap": 0x4}
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True, interval=0.1):
         super().__init__(daemon=True)
+        self.interval = interval
         self.samples, self.reasons = [], set()
         self.sm_max = None
         self.stop_flag = False
         self.ok = False
         try:
+            if not enabled:
+                raise RuntimeError("disabled")
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
@@ -164,7 +167,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(self.interval)
 
     def summary(self):
         if not self.samples:
@@ -187,7 +190,7 @@ def build_problem(M, wl, numerics):
         u0 = np.zeros(3)
         return pot, proposer, accepter, u0
     g = np.load(os.path.join(ROOT, "tests", "golden", "lorenz_problem_K6_J4.npz"))
-    f = M.Lorenz96Moments(6, 4, wl["T"], 1.0, g["prior_means"], g["IC"])
+    f = M.Lorenz96Moments(6, 4, wl["T"], 1.0, g["prior_means"], g["IC"], numerics=numerics)
     prior = M.GaussianDistribution(np.zeros(3), np.diag([10., 1, 10]))
     pot = M.EvolutionPotential(f, g["y"], M.GaussianDistribution(np.zeros(30), 0.25 * np.diag(g["var"])))
     proposer = M.ConstStepStandardRWProposer(wl["delta"], prior)
@@ -266,7 +269,9 @@ def main():
             chains.run(spec, S, trace=trace)
         torch.cuda.synchronize()
         c0 = chains.counters.sum(0).cpu().numpy()
-        sampler_clk = ClockSampler(local)                  # NVML init happens here, before the barrier
+        # NVML init happens here, before the barrier.  Every rank samples its own GPU (rank 0 at 10 Hz for
+        # the contract's `clocks` key, the others at 4 Hz: enough to tell a slow GPU from a slow host)
+        sampler_clk = ClockSampler(local, interval=0.1 if rank == 0 else 0.25)
         if world > 1:
             parallel.allreduce_pooled(chains.pooled(), 3)   # warm NCCL with the message of the final reduce
             dist.barrier()
@@ -282,7 +287,10 @@ def main():
             ev[k][1].record()
             kept.append(trace[:trace_chains].clone())
         ev[K][0].record()
-        pooled = parallel.allreduce_pooled(chains.pooled(), 3)  # the only collective of the job
+        pooled_local = chains.pooled()
+        ev_mid = torch.cuda.Event(enable_timing=True)
+        ev_mid.record()
+        pooled = parallel.allreduce_pooled(pooled_local, 3)  # the only collective of the job
         ev[K][1].record()
         torch.cuda.synchronize()
         if world > 1:
@@ -293,7 +301,16 @@ def main():
         sampler_clk.join()
         kern_ms = [a.elapsed_time(b) for a, b in ev[:K]]
         red_ms = ev[K][0].elapsed_time(ev[K][1])
+        pool_ms = ev[K][0].elapsed_time(ev_mid)
         total_ms = parallel.max_over_ranks(sum(kern_ms) + red_ms, dev)
+        clk = sampler_clk.summary() or dict(sm_mhz=float("nan"), reasons=[])
+        per_rank = torch.tensor([sum(kern_ms), red_ms, t_wall * 1e3, clk["sm_mhz"], float(len(clk["reasons"])),
+                                 max(kern_ms), min(kern_ms)], dtype=F64, device=dev)
+        if world > 1:
+            gathered = [torch.zeros_like(per_rank) for _ in range(world)]
+            dist.all_gather(gathered, per_rank)
+            per_rank = torch.stack(gathered)
+        per_rank = per_rank.reshape(-1, 7).cpu().numpy().round(3).tolist()
         c1 = chains.counters.sum(0).cpu().numpy()
         dc = (c1 - c0).astype(np.float64)
         cnt = torch.tensor(dc, dtype=F64, device=dev)
@@ -309,7 +326,7 @@ def main():
         tr = torch.stack(kept, dim=1).reshape(min(trace_chains, B), K * S, 3).cpu().numpy()
         ess_tot, ess_per = M.stats.ess_multichain(tr)
         ess_per_chain = ess_tot / tr.shape[0]
-        out = dict(value=value, total_ms=total_ms, kern_ms=kern_ms, red_ms=red_ms, achieved=achieved,
+        out = dict(value=value, total_ms=total_ms, kern_ms=kern_ms, red_ms=red_ms, pool_ms=pool_ms, per_rank=per_rank, achieved=achieved,
                    hbm_gbs=hbm_bytes / (sum(kern_ms) * 1e-3) / 1e9, counters=dc_all, steps_all=steps_all,
                    acceptance=dc_all[1] / max(dc_all[0], 1), ess_per_sec=ess_per_chain * B * world / (total_ms * 1e-3),
                    ess_per_chain=ess_per_chain, clocks=sampler_clk.summary(), launches=chains.launches - launches0,
@@ -336,7 +353,13 @@ def main():
         return out
 
     peak = M.fp64_peak_tflops(5)
-    res = measure(wl, args.steps, max(args.warmup, 3), burn_in=args.burn_in if wl['model'] == 'burgers' else 0)
+    burn_in, start = (args.burn_in if wl['model'] == 'burgers' else 0), None
+    if wl['model'] == 'burgers' and wl['N'] >= 1024:
+        # a solve costs ~30 MFLOP here: start near the posterior (like the extra-workload leg) and keep
+        # the untimed burn-in short
+        burn_in, start = min(burn_in, 200), TRUTH - PRIOR_MEAN
+    args.burn_in = burn_in
+    res = measure(wl, args.steps, max(args.warmup, 3), burn_in=burn_in, start=start)
     extra = {}
     if not args.no_extra and world == 1 and args.workload == "burgers_pcn_256":
         for name in ("lorenz_rw", "burgers_pcn_1024"):
@@ -374,7 +397,10 @@ def main():
                 config=workload_config(wl, args.workload, args), roofline=roofline, e2e=res.get("e2e"),
                 gpu_launches=int(res["launches"]), clocks=res["clocks"], ess_per_sec=res["ess_per_sec"],
                 ess_per_chain_in_timed_window=res["ess_per_chain"], acceptance_rate=res["acceptance"],
-                mean_work_per_solve=res["mean_work_per_solve"], allreduce_ms=res["red_ms"],
+                mean_work_per_solve=res["mean_work_per_solve"], allreduce_ms=res["red_ms"], pool_moments_ms=res["pool_ms"],
+                kernel_ms_per_step=[round(x, 3) for x in res["kern_ms"]],
+                per_rank_ms=dict(columns=["sum_kernel", "final_reduce", "wall_timed_region", "sm_mhz", "n_throttle_reasons",
+                                          "slowest_launch", "fastest_launch"], rows=res["per_rank"]),
                 posterior_mean=[float(x) for x in res["pooled"][1:4]], extra_workloads=extra)
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1

@@ -113,7 +113,8 @@ typedef struct ipmcmc_burgers_desc {
 typedef struct ipmcmc_lorenz_desc {
     int32_t K, J;             /* slow variables / fast variables per slow variable              */
     int32_t max_attempts;     /* cap on RK attempts per solve (<=0: 1<<20)                      */
-    int32_t reserved;
+    int32_t numerics;         /* IPMCMC_NUMERICS_EXACT: right-hand side in the reference's rounding
+                                 order (lorenz.py:73-101); IPMCMC_NUMERICS_FUSED: contracted RHS  */
     double T;                 /* integration horizon per solve                                  */
     double c;                 /* fixed time-scale parameter                                     */
     double rtol, atol;        /* solve_ivp defaults 1e-3, 1e-6                                  */
@@ -240,11 +241,11 @@ int ipmcmc_sample_host(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, int64_t 
  * Probes used by the parity tests and the roofline measurement
  * ------------------------------------------------------------------------------------------ */
 /* Lorenz-96 RHS for n states (lorenz.py:44-101): theta_dev [n,4] = (F,h,c,b). */
-int ipmcmc_lorenz_rhs(int32_t K, int32_t J, int64_t n, const double *theta_dev,
+int ipmcmc_lorenz_rhs(int32_t K, int32_t J, int32_t numerics, int64_t n, const double *theta_dev,
                       const double *state_dev, double *rhs_dev, void *stream);
 /* One Dormand-Prince attempt (scipy rk.py:14-72,111-116) for n states with step h_dev[n]:
    out_dev [n, 2*n_var + 1] = (y_new, f_new, error_norm). */
-int ipmcmc_lorenz_rk45_attempt(int32_t K, int32_t J, int64_t n, const double *theta_dev,
+int ipmcmc_lorenz_rk45_attempt(int32_t K, int32_t J, int32_t numerics, int64_t n, const double *theta_dev,
                                const double *state_dev, const double *h_dev, double rtol,
                                double atol, double *out_dev, void *stream);
 /* Engine RNG: out_dev [n_chains, n_steps, d + 1] = (normals xi_0..xi_{d-1}, uniform U). */

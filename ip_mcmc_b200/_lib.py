@@ -32,7 +32,7 @@ class BurgersDesc(C.Structure):
 
 
 class LorenzDesc(C.Structure):
-    _fields_ = [("K", C.c_int32), ("J", C.c_int32), ("max_attempts", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("K", C.c_int32), ("J", C.c_int32), ("max_attempts", C.c_int32), ("numerics", C.c_int32),
                 ("T", C.c_double), ("c", C.c_double), ("rtol", C.c_double), ("atol", C.c_double),
                 ("param_mean", c_double_p), ("potential", PotentialDesc)]
 
@@ -70,9 +70,9 @@ SYMBOLS = {
                                       C.c_void_p, C.c_void_p]),
     "ipmcmc_sample_host": (C.c_int, [C.c_void_p, C.POINTER(SamplerDesc), C.c_int64, C.c_int64, c_double_p,
                                      c_double_p, c_double_p, C.c_int64, c_int64_p, c_double_p, C.c_void_p]),
-    "ipmcmc_lorenz_rhs": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+    "ipmcmc_lorenz_rhs": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
-    "ipmcmc_lorenz_rk45_attempt": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+    "ipmcmc_lorenz_rk45_attempt": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "ipmcmc_rng_probe": (C.c_int, [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                    C.c_void_p, C.c_void_p]),
@@ -89,7 +89,9 @@ class EngineError(RuntimeError):
 
 
 def lib_path():
-    return _build.LIB
+    # IPMCMC_LIB: developer override used by tools/build_variants.py for A/B measurements of kernel
+    # variants (same ABI, same sources, different -D switches)
+    return os.environ.get("IPMCMC_LIB") or _build.LIB
 
 
 def load():

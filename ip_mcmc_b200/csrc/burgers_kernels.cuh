@@ -7,6 +7,10 @@
 #include "burgers_team.cuh"
 #include "sampler.cuh"
 
+#ifndef IPMCMC_CHAIN_MINB
+#define IPMCMC_CHAIN_MINB 2   // register budget of the chain kernel: 2 -> 128, 1 -> 255 registers per thread
+#endif
+
 namespace ipmcmc {
 
 // shared memory layout per warp: state[N] | G[MAX_OBS] | r2[MAX_OBS]
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(256) burgers_forward_kernel(const __grid_const
 // W warps per CTA, one chain per warp.  Warps never synchronise with each other; the CTA shape
 // only pins which chains share an SM sub-partition (warp w -> SMSP w % 4).
 template <int CPL, int NUMERICS, bool PADDED>
-__global__ void __launch_bounds__(256) burgers_chain_kernel(const __grid_constant__ BurgersDev B,
+__global__ void __launch_bounds__(256, IPMCMC_CHAIN_MINB) burgers_chain_kernel(const __grid_constant__ BurgersDev B,
                                                             const __grid_constant__ SamplerDev S,
                                                             const __grid_constant__ ChainBufDev C, long long n_chains,
                                                             long long n_steps) {

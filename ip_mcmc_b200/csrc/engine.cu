@@ -168,6 +168,11 @@ extern "C" int ipmcmc_lorenz_create(const ipmcmc_lorenz_desc *d, ipmcmc_problem 
     l.J = d->J;
     l.nvar = d->K * (d->J + 1);
     l.max_attempts = d->max_attempts > 0 ? d->max_attempts : (1 << 20);
+    if (d->numerics != IPMCMC_NUMERICS_EXACT && d->numerics != IPMCMC_NUMERICS_FUSED) {
+        delete p;
+        return fail(IPMCMC_EINVAL, "bad numerics");
+    }
+    p->numerics = d->numerics;
     l.T = d->T;
     l.c = d->c;
     l.rtol = d->rtol;
@@ -260,13 +265,39 @@ static int burgers_launch_team_chain(ipmcmc_problem *p, const SamplerDev &S, con
         return fail(IPMCMC_EUNSUPPORTED, "no kernel for n_cells=%d", p->b.N);           \
     } while (0)
 
-#define LORENZ_DISPATCH(KERNEL, J, ...)                                                 \
+// CTA shape of the Lorenz kernels.  Batches that fit one wave get one CTA of W = ceil(warps / n_SM)
+// warps per SM, so that the warps of an SM are dealt round-robin onto its four sub-partitions
+// (warp w -> sub-partition w % 4); larger batches use 4-warp CTAs and the block scheduler.
+static int lorenz_warps_per_cta(long long warps, int K) {
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    int wpc = warps <= 8LL * n_sm ? (int)((warps + n_sm - 1) / n_sm) : 4;
+    if (const char *e = getenv("IPMCMC_LORENZ_WPC")) wpc = atoi(e) > 0 && atoi(e) <= 8 ? atoi(e) : wpc;  // experiments
+    const int fit = (int)((48 * 1024) / lorenz_smem_bytes(K));   // default dynamic shared memory limit
+    if (wpc > fit) wpc = fit;
+    return wpc < 1 ? 1 : wpc;
+}
+
+// J in {1,2,4,8}; K = 6 (the reference's problem) is specialised at compile time, any other K
+// runs the generic lane-group code; NUM = IPMCMC_NUMERICS_*.
+#define LORENZ_DISPATCH_JK(KERNEL, J, KT, NUM, ...)                                     \
     do {                                                                                \
+        if ((NUM) == IPMCMC_NUMERICS_FUSED) KERNEL<J, KT, LNUM_FUSED> __VA_ARGS__;      \
+        else KERNEL<J, KT, LNUM_EXACT> __VA_ARGS__;                                     \
+    } while (0)
+#define LORENZ_DISPATCH(KERNEL, J, K, NUM, ...)                                         \
+    do {                                                                                \
+        if ((NUM) != IPMCMC_NUMERICS_EXACT && (NUM) != IPMCMC_NUMERICS_FUSED)           \
+            return fail(IPMCMC_EINVAL, "bad numerics");                                 \
         switch (J) {                                                                    \
-            case 1: KERNEL<1> __VA_ARGS__; break;                                       \
-            case 2: KERNEL<2> __VA_ARGS__; break;                                       \
-            case 4: KERNEL<4> __VA_ARGS__; break;                                       \
-            case 8: KERNEL<8> __VA_ARGS__; break;                                       \
+            case 1: LORENZ_DISPATCH_JK(KERNEL, 1, 0, NUM, __VA_ARGS__); break;          \
+            case 2: LORENZ_DISPATCH_JK(KERNEL, 2, 0, NUM, __VA_ARGS__); break;          \
+            case 4:                                                                     \
+                if ((K) == 6) LORENZ_DISPATCH_JK(KERNEL, 4, 6, NUM, __VA_ARGS__);       \
+                else LORENZ_DISPATCH_JK(KERNEL, 4, 0, NUM, __VA_ARGS__);                \
+                break;                                                                  \
+            case 8: LORENZ_DISPATCH_JK(KERNEL, 8, 0, NUM, __VA_ARGS__); break;          \
             default: return fail(IPMCMC_EUNSUPPORTED, "J=%d not in {1,2,4,8}", J);      \
         }                                                                               \
         CUDA_TRY(cudaGetLastError());                                                   \
@@ -284,10 +315,11 @@ extern "C" int ipmcmc_forward(ipmcmc_problem *p, int64_t n, const double *u_dev,
     }
     if (!state_dev) return fail(IPMCMC_EINVAL, "Lorenz forward needs state_dev (carried initial condition)");
     const int groups = lorenz_groups(p->l.K);
-    const long long blocks = (n + groups - 1) / groups;
-    LORENZ_DISPATCH(lorenz_forward_kernel, p->l.J,
-                    <<<grid_for(blocks), 32, lorenz_smem_bytes(p->l.K), st>>>(p->l, n, u_dev, G_dev, phi_dev, state_dev,
-                                                                              (long long *)work_dev));
+    const long long warps = (n + groups - 1) / groups;
+    const int wpc = lorenz_warps_per_cta(warps, p->l.K);
+    LORENZ_DISPATCH(lorenz_forward_kernel, p->l.J, p->l.K, p->numerics,
+                    <<<grid_for((warps + wpc - 1) / wpc), 32 * wpc, wpc * lorenz_smem_bytes(p->l.K), st>>>(
+                        p->l, n, u_dev, G_dev, phi_dev, state_dev, (long long *)work_dev));
     return 0;
 }
 
@@ -377,9 +409,11 @@ extern "C" int ipmcmc_run(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, const
         BURGERS_DISPATCH(burgers_launch_chain, p, S, C, n_chains, n_steps, wpc, st);
     }
     const int groups = lorenz_groups(p->l.K);
-    const long long blocks = (n_chains + groups - 1) / groups;
-    LORENZ_DISPATCH(lorenz_chain_kernel, p->l.J,
-                    <<<grid_for(blocks), 32, lorenz_smem_bytes(p->l.K), st>>>(p->l, S, C, n_chains, n_steps));
+    const long long warps = (n_chains + groups - 1) / groups;
+    const int wpc = lorenz_warps_per_cta(warps, p->l.K);
+    LORENZ_DISPATCH(lorenz_chain_kernel, p->l.J, p->l.K, p->numerics,
+                    <<<grid_for((warps + wpc - 1) / wpc), 32 * wpc, wpc * lorenz_smem_bytes(p->l.K), st>>>(
+                        p->l, S, C, n_chains, n_steps));
     return 0;
 }
 
@@ -491,24 +525,24 @@ extern "C" int ipmcmc_sample_host(ipmcmc_problem *p, const ipmcmc_sampler_desc *
 // ------------------------------------------------------------------------------------------------
 // probes
 // ------------------------------------------------------------------------------------------------
-extern "C" int ipmcmc_lorenz_rhs(int32_t K, int32_t J, int64_t n, const double *theta_dev, const double *state_dev,
+extern "C" int ipmcmc_lorenz_rhs(int32_t K, int32_t J, int32_t numerics, int64_t n, const double *theta_dev, const double *state_dev,
                                  double *rhs_dev, void *stream) {
     if (K < 1 || K > 32) return fail(IPMCMC_EUNSUPPORTED, "K=%d outside [1,32]", K);
     if (n <= 0) return 0;
     const int groups = lorenz_groups(K);
     const long long blocks = (n + groups - 1) / groups;
-    LORENZ_DISPATCH(lorenz_rhs_kernel, J, <<<grid_for(blocks), 32, 0, (cudaStream_t)stream>>>(K, n, theta_dev, state_dev, rhs_dev));
+    LORENZ_DISPATCH(lorenz_rhs_kernel, J, K, numerics, <<<grid_for(blocks), 32, 0, (cudaStream_t)stream>>>(K, n, theta_dev, state_dev, rhs_dev));
     return 0;
 }
 
-extern "C" int ipmcmc_lorenz_rk45_attempt(int32_t K, int32_t J, int64_t n, const double *theta_dev,
+extern "C" int ipmcmc_lorenz_rk45_attempt(int32_t K, int32_t J, int32_t numerics, int64_t n, const double *theta_dev,
                                           const double *state_dev, const double *h_dev, double rtol, double atol,
                                           double *out_dev, void *stream) {
     if (K < 1 || K > 32) return fail(IPMCMC_EUNSUPPORTED, "K=%d outside [1,32]", K);
     if (n <= 0) return 0;
     const int groups = lorenz_groups(K);
     const long long blocks = (n + groups - 1) / groups;
-    LORENZ_DISPATCH(lorenz_attempt_kernel, J,
+    LORENZ_DISPATCH(lorenz_attempt_kernel, J, K, numerics,
                     <<<grid_for(blocks), 32, 0, (cudaStream_t)stream>>>(K, n, theta_dev, state_dev, h_dev, rtol, atol, out_dev));
     return 0;
 }

@@ -49,13 +49,45 @@ __device__ __forceinline__ double rcp_newton(double x) {
 struct LorenzTheta {
     double F, h, c, b;
     double hc, hJ;  // h*c (lorenz.py:42) and h/J (lorenz.py:98), hoisted out of the RHS
+    double nbc, chJ, nhcJ;  // FUSED numerics: -b*c, c*h/J, -h*c/J
     __device__ __forceinline__ void finish(int J) {
         hc = h * c;
         hJ = h / (double)J;
+        nbc = -(b * c);
+        chJ = c * hJ;
+        nhcJ = -(hc / (double)J);
     }
 };
 
-template <int J>
+// x^(-1/10) for x in [1e-30, 1e30]: fp32 seed on the SFU (MUFU.LG2 / MUFU.EX2, relative error ~1e-6)
+// and two Newton rounds y <- y + y*(1 - x*y^10)/10 (error -> 5.5 e^2 each): ~1 ulp, 14 fp64
+// instructions in a chain of 12, instead of the ~70-instruction log + exp of pow().
+__device__ __forceinline__ double pow_m01(double x) {
+    double y = (double)exp2f(-0.1f * __log2f((float)x));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double y2 = y * y, y4 = y2 * y2, y8 = y4 * y4, y10 = y8 * y2;
+        const double r = fma(-x, y10, 1.0);
+        y = fma(y * 0.1, r, y);
+    }
+    return y;
+}
+
+// SAFETY * error_norm ** (-1/5) (scipy rk.py:157,166) from the SQUARED norm e2 = error_norm^2.
+// Outside [1e-30, 1e30] the caller's clamps (MIN_FACTOR 0.2, MAX_FACTOR 10) decide anyway, so the
+// argument is clamped first; NaN stays NaN (a NaN error norm rejects the step and shrinks h by
+// MIN_FACTOR, as in scipy: nan < 1 is False, max(0.2, nan) is 0.2).
+__device__ __forceinline__ double rk_raw_factor(double e2) {
+    const double x = fmin(fmax(e2, 1e-30), 1e30);
+    const double f = RK_SAFETY * pow_m01(x);
+    return (e2 != e2) ? e2 : f;
+}
+
+// KT: K known at compile time (6 = the reference's problem) or 0 = run-time K.
+// NUM: NUM_EXACT (reference rounding order in the RHS) or NUM_FUSED (contracted RHS).
+enum : int { LNUM_EXACT = 0, LNUM_FUSED = 1 };
+
+template <int J, int KT = 0, int NUM = LNUM_EXACT>
 struct LorenzLanes {
     static constexpr int NV = J + 1;  // variables per lane: y[0] = X_k, y[1+j] = Y_{k,j}
     int src_m1, src_m2, src_p1;       // absolute lane ids of X_{k-1}, X_{k-2}, X_{k+1}
@@ -75,7 +107,21 @@ struct LorenzLanes {
 
     // sum over the K lanes of the group: shuffle-down tree into the group's first lane, then one
     // broadcast, so every lane of the chain holds the SAME bits (control flow stays group-uniform)
+    // K known at compile time: every lane gathers the K partial sums with K independent
+    // shuffles and adds them as a balanced tree in lane order (identical bits on every lane, ~3
+    // dependent DADDs) instead of log2(K) dependent shuffle+add rounds plus a broadcast.
     __device__ __forceinline__ double group_sum(double v) const {
+        if (KT > 0) {
+            constexpr int KG = KT > 0 ? KT : 1;
+            double g[KG];
+#pragma unroll
+            for (int i = 0; i < KG; ++i) g[i] = __shfl_sync(FULL, v, base + i);
+#pragma unroll
+            for (int w = 1; w < KG; w *= 2)
+#pragma unroll
+                for (int i = 0; i + w < KG; i += 2 * w) g[i] = g[i] + g[i + w];
+            return g[0];
+        }
         double s = v;
         for (int off = 1; off < K; off *= 2) {
             const double t = __shfl_down_sync(FULL, s, off);
@@ -84,8 +130,40 @@ struct LorenzLanes {
         return __shfl_sync(FULL, s, base);
     }
 
+    // FUSED numerics: the same right-hand side contracted for the fp64 pipe (24 instead of 45
+    // instructions at J = 4):
+    //   dY_j = c*(-Y_j - b*Y_{j+1}*(Y_{j+2} - Y_{j-1}) + (h/J) X) = fma(-bc*Y_{j+1}, Y_{j+2}-Y_{j-1}, fma(-c, Y_j, (ch/J) X))
+    //   dX   = F - X - X_{k-1}*(X_{k-2} - X_{k+1}) - (hc/J) sum_j Y_j
+    __device__ __forceinline__ void rhs_fused(const LorenzTheta &th, const double (&y)[NV], double (&dy)[NV]) const {
+        const double X = y[0];
+        const double Xm1 = __shfl_sync(FULL, X, src_m1);
+        const double Xm2 = __shfl_sync(FULL, X, src_m2);
+        const double Xp1 = __shfl_sync(FULL, X, src_p1);
+        double out = th.F - X;
+        if (J > 0) {
+            const double A = th.chJ * X;
+            double g[J], t[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) g[j] = th.nbc * y[1 + j];
+#pragma unroll
+            for (int j = 0; j < J; ++j) t[j] = y[1 + j];
+#pragma unroll
+            for (int w = 1; w < J; w *= 2)
+#pragma unroll
+                for (int j = 0; j + w < J; j += 2 * w) t[j] = t[j] + t[j + w];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const double e = y[1 + (j + 2) % J] - y[1 + (j + J - 1) % J];
+                dy[1 + j] = fma(g[(j + 1) % J], e, fma(-th.c, y[1 + j], A));
+            }
+            out = fma(th.nhcJ, t[0], out);
+        }
+        dy[0] = fma(-Xm1, Xm2 - Xp1, out);
+    }
+
     // d(state)/dt in the reference's rounding order (lorenz.py:73-101)
     __device__ __forceinline__ void rhs(const LorenzTheta &th, const double (&y)[NV], double (&dy)[NV]) const {
+        if (NUM == LNUM_FUSED) return rhs_fused(th, y, dy);
         const double X = y[0];
         const double Xm1 = __shfl_sync(FULL, X, src_m1);
         const double Xm2 = __shfl_sync(FULL, X, src_m2);
@@ -118,17 +196,21 @@ struct LorenzLanes {
     }
 
     // RMS norm over the chain's n = K*(J+1) variables of v/scale (scipy common.py:63-65)
-    __device__ __forceinline__ double rms(const double (&v)[NV], double inv_sqrt_n) const {
+    __device__ __forceinline__ double sumsq(const double (&v)[NV]) const {
         double ss = 0.0;
 #pragma unroll
         for (int i = 0; i < NV; ++i) ss = fma(v[i], v[i], ss);
-        return sqrt(group_sum(ss)) * inv_sqrt_n;
+        return group_sum(ss);
+    }
+    __device__ __forceinline__ double rms(const double (&v)[NV], double inv_sqrt_n) const {
+        return sqrt(sumsq(v)) * inv_sqrt_n;
     }
 
     // One Dormand-Prince attempt (scipy rk.py:14-72 + error norm :111-116).
     // k1 = f(y) on entry; k7 = f(y_new) on exit.  Stage sums use FMA chains.
+    // Returns the SUM OF SQUARES of error/scale over the chain's variables (error_norm^2 * n).
     __device__ __forceinline__ double attempt(const LorenzTheta &th, const double (&y)[NV], const double (&k1)[NV],
-                                              double h, double rtol, double atol, double inv_sqrt_n,
+                                              double h, double rtol, double atol,
                                               double (&ynew)[NV], double (&k7)[NV]) const {
         double k2[NV], k3[NV], k4[NV], k5[NV], k6[NV], ys[NV];
 #pragma unroll
@@ -164,12 +246,12 @@ struct LorenzLanes {
             const double scale = fma(absmax_bits(y[i], ynew[i]), rtol, atol);
             e[i] = err * rcp_newton(scale);
         }
-        return rms(e, inv_sqrt_n);
+        return sumsq(e);
     }
 };
 
 // Per-chain integrator state for the lock-step solve.
-template <int J>
+template <int J, int KT = 0, int NUM = LNUM_EXACT>
 struct LorenzSolve {
     static constexpr int NV = J + 1;
     double y[NV], f[NV];
@@ -190,8 +272,10 @@ struct LorenzSolve {
 
     // solve_ivp(fun, (0,T), y0, 'RK45'): initial step (common.py:68-140), then steps until t == T.
     // `active`: this lane's chain takes part (others run predicated-off). All 32 lanes must call.
-    __device__ __forceinline__ void solve(const LorenzLanes<J> &L, const LorenzDev &P, const LorenzTheta &th, bool active) {
+    __device__ __forceinline__ void solve(const LorenzLanes<J, KT, NUM> &L, const LorenzDev &P, const LorenzTheta &th,
+                                          bool active) {
         const double inv_sqrt_n = 1.0 / sqrt((double)P.nvar);
+        const double inv_n = 1.0 / (double)P.nvar;
         t = 0.0;
         n_t = n_acc = n_rej = 0;
 #pragma unroll
@@ -240,28 +324,34 @@ struct LorenzSolve {
             h = t_new - t;
             const double h_abs_used = fabs(h);
             double ynew[NV], fnew[NV];
-            const double err = L.attempt(th, y, f, h, P.rtol, P.atol, inv_sqrt_n, ynew, fnew);
-            if (!done && !fail) {
-                if (err < 1.0) {
-                    double factor = (err == 0.0) ? RK_MAX_FACTOR : fmin(RK_MAX_FACTOR, RK_SAFETY * exp(-0.2 * log(err)));
-                    if (step_rejected) factor = fmin(1.0, factor);
-                    h_abs = h_abs_used * factor;
-                    t = t_new;
+            // error_norm^2; the controller below is branch-free (chains of a warp accept and reject
+            // in the same attempt more often than not) and never takes the square root:
+            // error_norm < 1 <=> e2 < 1, error_norm^(-1/5) = e2^(-1/10)
+            const double e2 = L.attempt(th, y, f, h, P.rtol, P.atol, ynew, fnew) * inv_n;
+            const bool live = !done && !fail;
+            const bool acc = live && (e2 < 1.0);
+            const bool rej = live && !acc;   // NaN error norms land here too, as in scipy (nan < 1 is False)
+            const double raw = rk_raw_factor(e2);
+            double f_acc = (e2 == 0.0) ? RK_MAX_FACTOR : fmin(RK_MAX_FACTOR, raw);
+            if (step_rejected) f_acc = fmin(1.0, f_acc);
+            const double f_rej = fmax(RK_MIN_FACTOR, raw);
+            if (live) h_abs = h_abs_used * (acc ? f_acc : f_rej);
+            if (acc) {
+                t = t_new;
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) {
-                        y[i] = ynew[i];
-                        f[i] = fnew[i];
-                    }
-                    add_moments();
-                    ++n_acc;
-                    new_step = true;
-                    if (t == P.T) done = true;
-                } else {
-                    h_abs = h_abs_used * fmax(RK_MIN_FACTOR, RK_SAFETY * exp(-0.2 * log(err)));
-                    step_rejected = true;
-                    new_step = false;
-                    ++n_rej;   // NaN error norms land here too, as in scipy (nan < 1 is False)
+                for (int i = 0; i < NV; ++i) {
+                    y[i] = ynew[i];
+                    f[i] = fnew[i];
                 }
+                add_moments();
+                ++n_acc;
+                new_step = true;
+                if (t == P.T) done = true;
+            }
+            if (rej) {
+                step_rejected = true;
+                new_step = false;
+                ++n_rej;
             }
             ++guard;
             if (fail || guard >= P.max_attempts) done = true;

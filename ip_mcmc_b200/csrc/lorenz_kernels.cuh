@@ -12,14 +12,14 @@ __host__ __device__ inline size_t lorenz_smem_bytes(int K) {
     return (size_t)(lorenz_groups(K) + 1) * 2 * IPMCMC_MAX_OBS * sizeof(double);
 }
 
-template <int J>
-__device__ __forceinline__ void lorenz_load_state(const LorenzLanes<J> &L, const double *s, double (&y)[J + 1]) {
+template <int J, int KT, int NUM>
+__device__ __forceinline__ void lorenz_load_state(const LorenzLanes<J, KT, NUM> &L, const double *s, double (&y)[J + 1]) {
     y[0] = s[L.k];
 #pragma unroll
     for (int j = 0; j < J; ++j) y[1 + j] = s[L.K + L.k * J + j];
 }
-template <int J>
-__device__ __forceinline__ void lorenz_store_state(const LorenzLanes<J> &L, double *s, const double (&y)[J + 1]) {
+template <int J, int KT, int NUM>
+__device__ __forceinline__ void lorenz_store_state(const LorenzLanes<J, KT, NUM> &L, double *s, const double (&y)[J + 1]) {
     s[L.k] = y[0];
 #pragma unroll
     for (int j = 0; j < J; ++j) s[L.K + L.k * J + j] = y[1 + j];
@@ -28,8 +28,9 @@ __device__ __forceinline__ void lorenz_store_state(const LorenzLanes<J> &L, doub
 // LorenzObservationOperator.__call__ (lorenz_mcmc.py:55-68) + EvolutionPotential (potential.py:53-54)
 // for every chain of the warp at once.  `ui`: component i of the chain's u on group lane i.
 // S.y carries the initial condition in and the end state out (lorenz_mcmc.py:66).
-template <int J>
-__device__ __forceinline__ double lorenz_phi(const LorenzLanes<J> &L, const LorenzDev &P, double ui, LorenzSolve<J> &S,
+template <int J, int KT, int NUM>
+__device__ __forceinline__ double lorenz_phi(const LorenzLanes<J, KT, NUM> &L, const LorenzDev &P, double ui,
+                                          LorenzSolve<J, KT, NUM> &S,
                                           bool active, double *Gs, double *r2) {
     // F, h, b = prior_means + u   (lorenz_mcmc.py:64)
     const double pi = (L.k < 3) ? P.param_mean[L.k] + ui : 0.0;
@@ -55,29 +56,32 @@ __device__ __forceinline__ double lorenz_phi(const LorenzLanes<J> &L, const Lore
     return potential_from_G(P.pot, Gs, r2, L.k, L.K, FULL);
 }
 
-template <int J>
-__global__ void __launch_bounds__(32) lorenz_forward_kernel(const __grid_constant__ LorenzDev P, long long n,
+template <int J, int KT, int NUM>
+__global__ void __launch_bounds__(256, 1) lorenz_forward_kernel(const __grid_constant__ LorenzDev P, long long n,
                                                             const double *__restrict__ u, double *__restrict__ G,
                                                             double *__restrict__ phi, double *__restrict__ state,
                                                             long long *__restrict__ work) {
-    extern __shared__ double smem[];
+    extern __shared__ double smem_all[];
     const int lane = lane_id();
     const int groups = lorenz_groups(P.K);
-    LorenzLanes<J> L;
+    // W warps per CTA (warp w sits on SM sub-partition w % 4); warps never synchronise with each other
+    const int warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    double *smem = smem_all + (size_t)warp * (lorenz_smem_bytes(P.K) / sizeof(double));
+    LorenzLanes<J, KT, NUM> L;
     L.init(lane, P.K, groups);
     const int slot = L.valid ? lane / P.K : groups;
     double *Gs = smem + (size_t)slot * 2 * IPMCMC_MAX_OBS, *r2 = Gs + IPMCMC_MAX_OBS;
-    for (long long c0 = (long long)blockIdx.x * groups; c0 < n; c0 += (long long)gridDim.x * groups) {
+    for (long long c0 = ((long long)blockIdx.x * wpc + warp) * groups; c0 < n; c0 += (long long)gridDim.x * wpc * groups) {
         const long long c = c0 + slot;
         const bool active = L.valid && c < n;
-        LorenzSolve<J> S;
+        LorenzSolve<J, KT, NUM> S;
 #pragma unroll
         for (int i = 0; i < J + 1; ++i) S.y[i] = 0.0;
-        if (active) lorenz_load_state<J>(L, state + c * P.nvar, S.y);
+        if (active) lorenz_load_state<J, KT, NUM>(L, state + c * P.nvar, S.y);
         const double ui = (active && L.k < 3) ? u[c * 3 + L.k] : 0.0;
-        const double ph = lorenz_phi<J>(L, P, ui, S, active, Gs, r2);
+        const double ph = lorenz_phi<J, KT, NUM>(L, P, ui, S, active, Gs, r2);
         if (active) {
-            lorenz_store_state<J>(L, state + c * P.nvar, S.y);
+            lorenz_store_state<J, KT, NUM>(L, state + c * P.nvar, S.y);
             if (G)
                 for (int i = L.k; i < P.pot.q; i += P.K) G[c * P.pot.q + i] = Gs[i];
             if (L.k == 0) {
@@ -92,30 +96,33 @@ __global__ void __launch_bounds__(32) lorenz_forward_kernel(const __grid_constan
     }
 }
 
-template <int J>
-__global__ void __launch_bounds__(32) lorenz_chain_kernel(const __grid_constant__ LorenzDev P,
+template <int J, int KT, int NUM>
+__global__ void __launch_bounds__(256, 1) lorenz_chain_kernel(const __grid_constant__ LorenzDev P,
                                                           const __grid_constant__ SamplerDev Sd,
                                                           const __grid_constant__ ChainBufDev C, long long n_chains,
                                                           long long n_steps) {
-    extern __shared__ double smem[];
+    extern __shared__ double smem_all[];
     const int lane = lane_id();
     const int groups = lorenz_groups(P.K);
-    LorenzLanes<J> L;
+    const int warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    double *smem = smem_all + (size_t)warp * (lorenz_smem_bytes(P.K) / sizeof(double));
+    LorenzLanes<J, KT, NUM> L;
     L.init(lane, P.K, groups);
     const int slot = L.valid ? lane / P.K : groups;
     double *Gs = smem + (size_t)slot * 2 * IPMCMC_MAX_OBS, *r2 = Gs + IPMCMC_MAX_OBS;
     const Group Gp{L.base, P.K, L.k, FULL};
     const int d = Sd.d;  // 3
-    for (long long c0 = (long long)blockIdx.x * groups; c0 < n_chains; c0 += (long long)gridDim.x * groups) {
+    for (long long c0 = ((long long)blockIdx.x * wpc + warp) * groups; c0 < n_chains;
+         c0 += (long long)gridDim.x * wpc * groups) {
         const long long c = c0 + slot;
         const bool active = L.valid && c < n_chains;
         const long long cs = active ? c : 0;  // safe index for predicated-off lanes
         const long long cg = Sd.chain_offset + cs;
         const bool own = active && L.k < d;
-        LorenzSolve<J> S;
+        LorenzSolve<J, KT, NUM> S;
 #pragma unroll
         for (int i = 0; i < J + 1; ++i) S.y[i] = 0.0;
-        if (active) lorenz_load_state<J>(L, C.model_state + c * P.nvar, S.y);
+        if (active) lorenz_load_state<J, KT, NUM>(L, C.model_state + c * P.nvar, S.y);
         double ui = own ? C.u[c * d + L.k] : 0.0;
         double phi_u = active ? C.phi[c] : 0.0;
         long long cnt[CNT_N];
@@ -141,7 +148,7 @@ __global__ void __launch_bounds__(32) lorenz_chain_kernel(const __grid_constant_
             double ph_v = 0.0;
             for (int pass = __any_sync(FULL, need_u) ? 0 : 1; pass < 2; ++pass) {
                 const bool act = pass ? ok : need_u;
-                const double ph = lorenz_phi<J>(L, P, pass ? vi : ui, S, act, Gs, r2);
+                const double ph = lorenz_phi<J, KT, NUM>(L, P, pass ? vi : ui, S, act, Gs, r2);
                 if (act) {
                     if (pass) ph_v = ph; else phi_u = ph;
                     if (!pass) {
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(32) lorenz_chain_kernel(const __grid_constant_
             }
         }
         if (active) {
-            lorenz_store_state<J>(L, C.model_state + c * P.nvar, S.y);
+            lorenz_store_state<J, KT, NUM>(L, C.model_state + c * P.nvar, S.y);
             if (own) {
                 C.u[c * d + L.k] = ui;
                 C.mom_mean[c * d + L.k] = mom.mean;
@@ -210,13 +217,13 @@ __global__ void __launch_bounds__(32) lorenz_chain_kernel(const __grid_constant_
 }
 
 // ---- probes -------------------------------------------------------------------------------
-template <int J>
+template <int J, int KT, int NUM>
 __global__ void __launch_bounds__(32) lorenz_rhs_kernel(int K, long long n, const double *__restrict__ theta,
                                                         const double *__restrict__ state, double *__restrict__ out) {
     const int lane = lane_id();
     const int groups = lorenz_groups(K);
     const int nvar = K * (J + 1);
-    LorenzLanes<J> L;
+    LorenzLanes<J, KT, NUM> L;
     L.init(lane, K, groups);
     const int slot = L.valid ? lane / K : groups;
     for (long long c0 = (long long)blockIdx.x * groups; c0 < n; c0 += (long long)gridDim.x * groups) {
@@ -227,16 +234,16 @@ __global__ void __launch_bounds__(32) lorenz_rhs_kernel(int K, long long n, cons
         for (int i = 0; i < J + 1; ++i) y[i] = 0.0;
         LorenzTheta th{0, 0, 0, 0, 0, 0};
         if (active) {
-            lorenz_load_state<J>(L, state + c * nvar, y);
+            lorenz_load_state<J, KT, NUM>(L, state + c * nvar, y);
             th = LorenzTheta{theta[4 * c], theta[4 * c + 1], theta[4 * c + 2], theta[4 * c + 3], 0, 0};
         }
         th.finish(J);
         L.rhs(th, y, dy);
-        if (active) lorenz_store_state<J>(L, out + c * nvar, dy);
+        if (active) lorenz_store_state<J, KT, NUM>(L, out + c * nvar, dy);
     }
 }
 
-template <int J>
+template <int J, int KT, int NUM>
 __global__ void __launch_bounds__(32) lorenz_attempt_kernel(int K, long long n, const double *__restrict__ theta,
                                                             const double *__restrict__ state,
                                                             const double *__restrict__ hstep, double rtol, double atol,
@@ -244,7 +251,7 @@ __global__ void __launch_bounds__(32) lorenz_attempt_kernel(int K, long long n, 
     const int lane = lane_id();
     const int groups = lorenz_groups(K);
     const int nvar = K * (J + 1);
-    LorenzLanes<J> L;
+    LorenzLanes<J, KT, NUM> L;
     L.init(lane, K, groups);
     const int slot = L.valid ? lane / K : groups;
     const double inv_sqrt_n = 1.0 / sqrt((double)nvar);
@@ -257,17 +264,17 @@ __global__ void __launch_bounds__(32) lorenz_attempt_kernel(int K, long long n, 
         LorenzTheta th{0, 0, 0, 0, 0, 0};
         double h = 0.0;
         if (active) {
-            lorenz_load_state<J>(L, state + c * nvar, y);
+            lorenz_load_state<J, KT, NUM>(L, state + c * nvar, y);
             th = LorenzTheta{theta[4 * c], theta[4 * c + 1], theta[4 * c + 2], theta[4 * c + 3], 0, 0};
             h = hstep[c];
         }
         th.finish(J);
         L.rhs(th, y, f);
-        const double err = L.attempt(th, y, f, h, rtol, atol, inv_sqrt_n, yn, fn);
+        const double err = sqrt(L.attempt(th, y, f, h, rtol, atol, yn, fn)) * inv_sqrt_n;
         if (active) {
             double *o = out + c * (2 * nvar + 1);
-            lorenz_store_state<J>(L, o, yn);
-            lorenz_store_state<J>(L, o + nvar, fn);
+            lorenz_store_state<J, KT, NUM>(L, o, yn);
+            lorenz_store_state<J, KT, NUM>(L, o + nvar, fn);
             if (L.k == 0) o[2 * nvar] = err;
         }
     }

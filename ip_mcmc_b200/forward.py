@@ -139,7 +139,10 @@ class Lorenz96Moments(ForwardModel):
     n_params = 3
     stateful = True
 
-    def __init__(self, K, J, T, c, prior_means, IC, rtol=1e-3, atol=1e-6, max_attempts=0):
+    def __init__(self, K, J, T, c, prior_means, IC, rtol=1e-3, atol=1e-6, max_attempts=0, numerics="exact"):
+        if numerics not in ("exact", "fused"):
+            raise ValueError("numerics must be 'exact' or 'fused'")
+        self.numerics = numerics
         self.K, self.J = int(K), int(J)
         self.T = float(T)
         self.c = float(c)
@@ -156,6 +159,7 @@ class Lorenz96Moments(ForwardModel):
         d = _lib.LorenzDesc()
         d.K, d.J = self.K, self.J
         d.max_attempts = self.max_attempts
+        d.numerics = _lib.NUMERICS_FUSED if self.numerics == "fused" else _lib.NUMERICS_EXACT
         d.T, d.c, d.rtol, d.atol = self.T, self.c, self.rtol, self.atol
         d.param_mean = _lib.as_double_p(self.prior_means)
         keep += [self.prior_means]

@@ -99,7 +99,7 @@ def s_lorenz():
         th = torch.tensor([[float(g[f"case{i}_F"]), float(g[f"case{i}_h"]), float(g[f"case{i}_c"]), float(g[f"case{i}_b"])]] * 7, device="cuda", dtype=torch.float64)
         st = torch.tensor(np.stack([g[f"case{i}_state"]] * 7), device="cuda")
         out = torch.empty_like(st)
-        _lib.check(lib.ipmcmc_lorenz_rhs(K, J, 7, th.data_ptr(), st.data_ptr(), out.data_ptr(), None))
+        _lib.check(lib.ipmcmc_lorenz_rhs(K, J, 0, 7, th.data_ptr(), st.data_ptr(), out.data_ptr(), None))
         o = out.cpu().numpy()
         print("rhs", K, J, "eq", all(np.array_equal(o[k], g[f"case{i}_rhs"]) for k in range(7)), np.abs(o[0] - g[f"case{i}_rhs"]).max())
     p = gold("lorenz_problem_K6_J4.npz")
@@ -111,7 +111,7 @@ def s_lorenz():
     for h in (1e-3, 1e-2, 5e-2):
         yn, fn, err, _ = L.rk45_attempt(fun, 0.0, y0, fun(0, y0), h)
         out = torch.empty((1, 61), dtype=torch.float64, device="cuda")
-        _lib.check(lib.ipmcmc_lorenz_rk45_attempt(K, J, 1, torch.tensor([theta], device="cuda").data_ptr(), torch.tensor([y0], device="cuda").data_ptr(),
+        _lib.check(lib.ipmcmc_lorenz_rk45_attempt(K, J, 0, 1, torch.tensor([theta], device="cuda").data_ptr(), torch.tensor([y0], device="cuda").data_ptr(),
                                                   torch.tensor([h], device="cuda", dtype=torch.float64).data_ptr(), 1e-3, 1e-6, out.data_ptr(), None))
         o = out.cpu().numpy()[0]
         print("attempt h", h, "ynew rel", np.max(np.abs(o[:30] - yn) / np.abs(yn)), "fnew rel", np.max(np.abs(o[30:60] - fn) / np.abs(fn)), "err", o[60], err, abs(o[60] - err) / err)

@@ -43,7 +43,7 @@ elif what == "chainstats":
     sampler = M.MCMCSampler(proposer, accepter, np.random.default_rng(2))
     spec, pot, a = sampler._compile(10 ** 9, 0, 1, None)
     ch = M.ChainBatch(pot.problem(), u0, n_chains=n)
-    for burn in (0, 200, 1500, 4000):
+    for burn in (0, 200, 1500, 4000, 10000, 20000):
         if burn:
             ch.run(spec, burn - ch.step)
         c0 = ch.counters.clone()

@@ -19,10 +19,10 @@ def G():
     return gpu_common
 
 
-def _lorenz_setup(T, p=None):
+def _lorenz_setup(T, p=None, numerics="exact"):
     import ip_mcmc_b200 as M
     p = golden("lorenz_problem_K6_J4.npz") if p is None else p
-    f = M.Lorenz96Moments(6, 4, T, 1, p["prior_means"], p["IC"])
+    f = M.Lorenz96Moments(6, 4, T, 1, p["prior_means"], p["IC"], numerics=numerics)
     noise = M.GaussianDistribution(np.zeros(30), 0.5 ** 2 * np.diag(p["var"]))     # lorenz_mcmc.py:111-112
     prior = M.GaussianDistribution(np.zeros(3), np.diag([10., 1, 10]))            # lorenz_mcmc.py:115,119
     pot = M.EvolutionPotential(f, p["y"], noise)
@@ -39,7 +39,7 @@ def test_rhs_bit_identical_to_reference(G):
         th = G.cuda(np.tile([float(g[f"case{i}_{k}"]) for k in "Fhcb"], (n, 1)))
         st = G.cuda(np.tile(g[f"case{i}_state"], (n, 1)))
         out = torch.empty_like(st)
-        _lib.check(lib.ipmcmc_lorenz_rhs(K, J, n, th.data_ptr(), st.data_ptr(), out.data_ptr(), None))
+        _lib.check(lib.ipmcmc_lorenz_rhs(K, J, 0, n, th.data_ptr(), st.data_ptr(), out.data_ptr(), None))
         o = out.cpu().numpy()
         assert all(np.array_equal(o[k], g[f"case{i}_rhs"]) for k in range(n)), (K, J)
 
@@ -54,13 +54,35 @@ def test_reference_rhs_known_answers(G):
              ((2, 2), (1, 1, 1, 1), [2, 3, 4, 5, 6, 7], [-2.5, -10.5, 2, -8, 2.5, -11.5]),
              ((3, 1), (2, 1, 1, 1), [0, 0, 0, 0, 0, 0], [2, 2, 2, 0, 0, 0])]
     for (K, J), th, s, want in cases:
-        tht, st = G.cuda([th]), G.cuda([s])
+        for num in (0, 1):                        # exact and fused numerics (small integers: both exact)
+            tht, st = G.cuda([th]), G.cuda([s])
+            out = torch.empty_like(st)
+            _lib.check(lib.ipmcmc_lorenz_rhs(K, J, num, 1, tht.data_ptr(), st.data_ptr(), out.data_ptr(), None))
+            np.testing.assert_allclose(out.cpu().numpy()[0], want, rtol=1e-15, atol=1e-15)
+
+
+def test_fused_rhs_close_to_reference(G):
+    """FUSED numerics contract the right-hand side (FMAs, factored products): same function, a
+    few ulps of the largest term away from the reference's rounding order."""
+    from ip_mcmc_b200 import _lib
+    lib = _lib.load()
+    g = golden("lorenz_rhs.npz")
+    for i in range(int(g["n_cases"])):
+        K, J = int(g[f"case{i}_K"]), int(g[f"case{i}_J"])
+        n = 7
+        th = G.cuda(np.tile([float(g[f"case{i}_{k}"]) for k in "Fhcb"], (n, 1)))
+        st = G.cuda(np.tile(g[f"case{i}_state"], (n, 1)))
         out = torch.empty_like(st)
-        _lib.check(lib.ipmcmc_lorenz_rhs(K, J, 1, tht.data_ptr(), st.data_ptr(), out.data_ptr(), None))
-        np.testing.assert_allclose(out.cpu().numpy()[0], want, rtol=1e-15, atol=1e-15)
+        _lib.check(lib.ipmcmc_lorenz_rhs(K, J, 1, n, th.data_ptr(), st.data_ptr(), out.data_ptr(), None))
+        o = out.cpu().numpy()
+        ref = g[f"case{i}_rhs"]
+        scale = max(1.0, float(np.abs(g[f"case{i}_state"]).max()) ** 2 * 12)     # size of the largest term
+        for k in range(n):
+            np.testing.assert_allclose(o[k], ref, rtol=1e-13, atol=1e-14 * scale)
 
 
-def test_single_rk45_attempt_vs_scipy_restatement(G):
+@pytest.mark.parametrize("num", [0, 1])
+def test_single_rk45_attempt_vs_scipy_restatement(G, num):
     """One Dormand-Prince attempt: y_new, f_new and the RMS error norm against oracle/lorenz_np.py
     (bit-identical to scipy).  Device stage sums are FMA chains, scipy's are BLAS dots: agreement
     to 1e-12 relative (north_star 1e-10)."""
@@ -75,7 +97,7 @@ def test_single_rk45_attempt_vs_scipy_restatement(G):
     hs = 10 ** rng.uniform(-3, -1.3, n)
     out = torch.empty((n, 61), dtype=torch.float64, device="cuda")
     tht, st, ht = G.cuda(thetas), G.cuda(states), G.cuda(hs)
-    _lib.check(lib.ipmcmc_lorenz_rk45_attempt(K, J, n, tht.data_ptr(), st.data_ptr(), ht.data_ptr(), 1e-3, 1e-6,
+    _lib.check(lib.ipmcmc_lorenz_rk45_attempt(K, J, num, n, tht.data_ptr(), st.data_ptr(), ht.data_ptr(), 1e-3, 1e-6,
                                               out.data_ptr(), None))
     o = out.cpu().numpy()
     for i in range(n):
@@ -86,7 +108,8 @@ def test_single_rk45_attempt_vs_scipy_restatement(G):
         np.testing.assert_allclose(o[i, 60], err, rtol=1e-9)
 
 
-def test_short_solves_vs_reference(G):
+@pytest.mark.parametrize("numerics", ["exact", "fused"])
+def test_short_solves_vs_reference(G, numerics):
     """solve_ivp parity while chaos has not yet amplified rounding: same accepted/rejected step
     counts (controller decisions) and G / end state close to the reference's."""
     gs = golden("lorenz_solves.npz")
@@ -94,7 +117,7 @@ def test_short_solves_vs_reference(G):
         T = float(gs[f"case{i}_T"])
         if T > 2:
             continue
-        f, pot, _, p = _lorenz_setup(T)
+        f, pot, _, p = _lorenz_setup(T, numerics=numerics)
         r = f.batch(gs[f"case{i}_u"].reshape(1, 3), p["IC"].reshape(1, -1))
         acc, rej = r["work"][0].tolist()
         assert acc == int(gs[f"case{i}_n_t"]) - 1
