@@ -210,6 +210,15 @@ typedef struct ipmcmc_chain_buffers {
     const int32_t *slot_chain_dev; /* [n_slots]                                                  */
     int32_t n_slots;
     int32_t warps_per_cta;
+    /* optional scratch of the DYNAMIC STEP SCHEDULER (Burgers, N <= 1024; results do not depend on
+       it): int64 [sched_len >= 3*n_chains + 2], contents irrelevant on entry.  When given, persistent
+       warps take (chain, sched_chunk steps) work items from a FIFO of ready chains instead of a
+       fixed chain -> warp map, which keeps every SM sub-partition busy until the launch ends although
+       solve lengths are data dependent.  slot_chain_dev / warps_per_cta are then ignored.        */
+    int64_t *sched_dev;
+    int64_t sched_len;
+    int32_t sched_chunk;      /* Metropolis steps per work item (<=0: 1)                        */
+    int32_t reserved;
 } ipmcmc_chain_buffers;
 
 int ipmcmc_run(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, const ipmcmc_chain_buffers *b,

@@ -54,7 +54,8 @@ class ChainBuffers(C.Structure):
                 ("counters_dev", C.c_void_p), ("trace_dev", C.c_void_p), ("n_record", C.c_int64),
                 ("steplog_dev", C.c_void_p), ("vlog_dev", C.c_void_p), ("inject_w_dev", C.c_void_p),
                 ("inject_u_dev", C.c_void_p), ("slot_chain_dev", C.c_void_p), ("n_slots", C.c_int32),
-                ("warps_per_cta", C.c_int32)]
+                ("warps_per_cta", C.c_int32), ("sched_dev", C.c_void_p), ("sched_len", C.c_int64),
+                ("sched_chunk", C.c_int32), ("reserved", C.c_int32)]
 
 
 # every symbol include/ipmcmc.h declares

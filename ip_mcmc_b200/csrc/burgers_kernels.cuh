@@ -11,6 +11,10 @@
 #define IPMCMC_CHAIN_MINB 2   // register budget of the chain kernel: 2 -> 128, 1 -> 255 registers per thread
 #endif
 
+#ifndef IPMCMC_CHAIN_MINB
+#define IPMCMC_CHAIN_MINB 2   // register budget of the static chain kernel: 2 -> 128, 1 -> 255 registers per thread
+#endif
+
 namespace ipmcmc {
 
 // shared memory layout per warp: state[N] | G[MAX_OBS] | r2[MAX_OBS]
@@ -84,6 +88,78 @@ __global__ void __launch_bounds__(256) burgers_forward_kernel(const __grid_const
     }
 }
 
+// Registers of one chain between Metropolis steps.
+struct ChainRegs {
+    double ui, phi_u, reg_u;
+    Welford mom;
+    long long cnt[CNT_N];
+};
+
+// Number of recorded steps in [record_start, g): recorded are the g with (g - record_start + 1) % interval == 0
+// (sampler.py:23-28).
+__device__ __forceinline__ long long recorded_before(const SamplerDev &S, long long g) {
+    return (S.record_interval > 0 && g > S.record_start) ? (g - S.record_start) / S.record_interval : 0;
+}
+
+// ONE Metropolis step of chain c (local id; cg global id) at launch-local step s: proposal -> (box
+// constraint) -> solve -> Phi(v) -> accept/reject -> counters, logs, moments, trace.
+template <int CPL, int NUMERICS, bool PADDED>
+__device__ __forceinline__ void burgers_metropolis_step(const BurgersDev &B, const SamplerDev &S, const ChainBufDev &C,
+                                                        const Group &Gp, long long c, long long cg, long long s,
+                                                        long long n_steps, double *state, double *Gs, double *r2,
+                                                        ChainRegs &R) {
+    const int lane = Gp.lane, d = S.d;
+    const long long gstep = S.first_step + s;
+    double ca, cb;
+    step_coefs(S, gstep, ca, cb);
+    const double w = proposal_noise(S, C, Gp, c, cg, s, n_steps, gstep);
+    const double vi = ca * R.ui + cb * w;
+    if (C.vlog && lane < d) C.vlog[(c * n_steps + s) * d + lane] = vi;
+    bool accepted = false;
+    double phi_v = nan(""), a = nan("");
+    int n_fv = 0;
+    const bool ok = !S.has_constraint || constraint_ok(S, Gp, vi);
+    if (ok) {
+        if (S.recompute_phi_u) {  // the reference's 2 solves per step (accepter.py:121-122)
+            int nf0;
+            R.phi_u = burgers_phi<CPL, NUMERICS, PADDED>(B, R.ui, state, Gs, r2, lane, nf0);
+            R.cnt[CNT_WORK_A] += nf0;
+            R.cnt[CNT_WORK_B] += 1;
+        }
+        phi_v = burgers_phi<CPL, NUMERICS, PADDED>(B, vi, state, Gs, r2, lane, n_fv);
+        R.cnt[CNT_WORK_A] += n_fv;
+        R.cnt[CNT_WORK_B] += 1;
+        double reg_v = 0.0;
+        if (S.accepter == IPMCMC_ACCEPT_RW) reg_v = prior_regulariser(S, Gp, vi);
+        a = exp((R.phi_u + R.reg_u) - (phi_v + reg_v));
+        const double U = C.inject_u ? C.inject_u[c * n_steps + s] : draw_uniform(S.seed, (uint64_t)cg, (uint64_t)gstep);
+        accepted = a > U;  // strict, un-clipped; NaN compares false (accepter.py:61-62)
+        if (!isfinite(phi_v)) R.cnt[CNT_NONFINITE] += 1;
+        if (accepted) {
+            R.ui = vi;
+            R.phi_u = phi_v;
+            R.reg_u = reg_v;
+        }
+    } else {
+        R.cnt[CNT_CONSTRAINT] += 1;
+    }
+    R.cnt[CNT_CALLS] += 1;
+    R.cnt[CNT_ACCEPTS] += accepted ? 1 : 0;
+    if (C.steplog && lane == 0) {
+        double *L = C.steplog + (c * n_steps + s) * 4;
+        L[0] = phi_v;
+        L[1] = a;
+        L[2] = accepted ? 1.0 : 0.0;
+        L[3] = (double)n_fv;
+    }
+    // recording (sampler.py:23-28)
+    if (S.record_interval > 0 && gstep >= S.record_start && ((gstep - S.record_start + 1) % S.record_interval) == 0) {
+        R.mom.add(R.ui);
+        const long long n_rec = recorded_before(S, gstep) - recorded_before(S, S.first_step);
+        if (C.trace && n_rec < C.n_record && lane < d) C.trace[(c * C.n_record + n_rec) * d + lane] = R.ui;
+    }
+}
+
 // W warps per CTA, one chain per warp.  Warps never synchronise with each other; the CTA shape
 // only pins which chains share an SM sub-partition (warp w -> SMSP w % 4).
 template <int CPL, int NUMERICS, bool PADDED>
@@ -103,86 +179,169 @@ __global__ void __launch_bounds__(256, IPMCMC_CHAIN_MINB) burgers_chain_kernel(c
         const long long c = C.slot_chain ? (long long)C.slot_chain[slot] : slot;
         if (c < 0 || c >= n_chains) continue;
         const long long cg = S.chain_offset + c;
-        double ui = (lane < d) ? C.u[c * d + lane] : 0.0;
-        double phi_u = C.phi[c];
-        long long cnt[CNT_N];
+        ChainRegs R;
+        R.ui = (lane < d) ? C.u[c * d + lane] : 0.0;
+        R.phi_u = C.phi[c];
 #pragma unroll
-        for (int k = 0; k < CNT_N; ++k) cnt[k] = 0;
-        int n_fv;
-        if (isnan(phi_u)) {  // first launch: Phi(u_0) not known yet
-            phi_u = burgers_phi<CPL, NUMERICS, PADDED>(B, ui, state, Gs, r2, lane, n_fv);
-            cnt[CNT_WORK_A] += n_fv;
-            cnt[CNT_WORK_B] += 1;
+        for (int k = 0; k < CNT_N; ++k) R.cnt[k] = 0;
+        if (isnan(R.phi_u)) {  // first launch: Phi(u_0) not known yet
+            int n_fv;
+            R.phi_u = burgers_phi<CPL, NUMERICS, PADDED>(B, R.ui, state, Gs, r2, lane, n_fv);
+            R.cnt[CNT_WORK_A] += n_fv;
+            R.cnt[CNT_WORK_B] += 1;
         }
-        double reg_u = (S.accepter == IPMCMC_ACCEPT_RW) ? prior_regulariser(S, Gp, ui) : 0.0;
-        Welford mom{C.mom_count[c], (lane < d) ? C.mom_mean[c * d + lane] : 0.0,
-                    (lane < d) ? C.mom_m2[c * d + lane] : 0.0};
-        long long n_rec = 0;
-
-        for (long long s = 0; s < n_steps; ++s) {
-            const long long gstep = S.first_step + s;
-            double ca, cb;
-            step_coefs(S, gstep, ca, cb);
-            const double w = proposal_noise(S, C, Gp, c, cg, s, n_steps, gstep);
-            const double vi = ca * ui + cb * w;
-            if (C.vlog && lane < d) C.vlog[(c * n_steps + s) * d + lane] = vi;
-            bool accepted = false;
-            double phi_v = nan(""), a = nan("");
-            n_fv = 0;
-            const bool ok = !S.has_constraint || constraint_ok(S, Gp, vi);
-            if (ok) {
-                if (S.recompute_phi_u) {  // the reference's 2 solves per step (accepter.py:121-122)
-                    int nf0;
-                    phi_u = burgers_phi<CPL, NUMERICS, PADDED>(B, ui, state, Gs, r2, lane, nf0);
-                    cnt[CNT_WORK_A] += nf0;
-                    cnt[CNT_WORK_B] += 1;
-                }
-                phi_v = burgers_phi<CPL, NUMERICS, PADDED>(B, vi, state, Gs, r2, lane, n_fv);
-                cnt[CNT_WORK_A] += n_fv;
-                cnt[CNT_WORK_B] += 1;
-                double reg_v = 0.0;
-                if (S.accepter == IPMCMC_ACCEPT_RW) reg_v = prior_regulariser(S, Gp, vi);
-                a = exp((phi_u + reg_u) - (phi_v + reg_v));
-                const double U = C.inject_u ? C.inject_u[c * n_steps + s]
-                                            : draw_uniform(S.seed, (uint64_t)cg, (uint64_t)gstep);
-                accepted = a > U;  // strict, un-clipped; NaN compares false (accepter.py:61-62)
-                if (!isfinite(phi_v)) cnt[CNT_NONFINITE] += 1;
-                if (accepted) {
-                    ui = vi;
-                    phi_u = phi_v;
-                    reg_u = reg_v;
-                }
-            } else {
-                cnt[CNT_CONSTRAINT] += 1;
-            }
-            cnt[CNT_CALLS] += 1;
-            cnt[CNT_ACCEPTS] += accepted ? 1 : 0;
-            if (C.steplog && lane == 0) {
-                double *L = C.steplog + (c * n_steps + s) * 4;
-                L[0] = phi_v;
-                L[1] = a;
-                L[2] = accepted ? 1.0 : 0.0;
-                L[3] = (double)n_fv;
-            }
-            // recording (sampler.py:23-28)
-            if (S.record_interval > 0 && gstep >= S.record_start &&
-                ((gstep - S.record_start + 1) % S.record_interval) == 0) {
-                mom.add(ui);
-                if (C.trace && n_rec < C.n_record && lane < d) C.trace[(c * C.n_record + n_rec) * d + lane] = ui;
-                ++n_rec;
-            }
-        }
+        R.reg_u = (S.accepter == IPMCMC_ACCEPT_RW) ? prior_regulariser(S, Gp, R.ui) : 0.0;
+        R.mom = Welford{C.mom_count[c], (lane < d) ? C.mom_mean[c * d + lane] : 0.0,
+                        (lane < d) ? C.mom_m2[c * d + lane] : 0.0};
+        for (long long s = 0; s < n_steps; ++s)
+            burgers_metropolis_step<CPL, NUMERICS, PADDED>(B, S, C, Gp, c, cg, s, n_steps, state, Gs, r2, R);
         // write back
         if (lane < d) {
-            C.u[c * d + lane] = ui;
-            C.mom_mean[c * d + lane] = mom.mean;
-            C.mom_m2[c * d + lane] = mom.m2;
+            C.u[c * d + lane] = R.ui;
+            C.mom_mean[c * d + lane] = R.mom.mean;
+            C.mom_m2[c * d + lane] = R.mom.m2;
         }
         if (lane == 0) {
-            C.phi[c] = phi_u;
-            C.mom_count[c] = mom.count;
+            C.phi[c] = R.phi_u;
+            C.mom_count[c] = R.mom.count;
 #pragma unroll
-            for (int k = 0; k < CNT_N; ++k) C.counters[c * CNT_N + k] += cnt[k];
+            for (int k = 0; k < CNT_N; ++k) C.counters[c * CNT_N + k] += R.cnt[k];
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dynamic step scheduler.  Solve lengths are data dependent and the warps of an SM do not all run
+// at the same speed (a warp alone on a sub-partition advances ~1.85x faster than one that shares
+// it), so a static chain -> warp map leaves sub-partitions idle at the end of a launch.  Here
+// persistent warps take (chain, `chunk` steps) work items from a FIFO of READY chains in global
+// memory: a chain is pushed back as soon as its item is done, so chains rotate over the warps,
+// advance at the same average pace and every warp stays busy until the queue runs dry.  The chain
+// state (u, Phi, moments: ~100 B) travels through L2 between items; Philox is keyed by (chain,
+// step), so the results do not depend on which warp ran which item (bit-identical to the static
+// kernel; tested).
+//
+// Scratch (caller-owned, int64): ring[cap] | progress[n_chains] | head | tail, cap = 2*n_chains.
+// Ring entry = ((lap+1) << 32) | chain for the ticket lap*cap + slot; 0 = consumed/empty.
+// ------------------------------------------------------------------------------------------------
+struct SchedView {
+    unsigned long long *ring, *head, *tail;
+    long long *progress;
+    long long cap;
+    __device__ __forceinline__ SchedView(long long *base, long long n_chains)
+        : ring((unsigned long long *)base), head((unsigned long long *)base + 3 * n_chains),
+          tail((unsigned long long *)base + 3 * n_chains + 1), progress(base + 2 * n_chains), cap(2 * n_chains) {}
+};
+__host__ __device__ inline long long sched_len(long long n_chains) { return 3 * n_chains + 2; }
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void sched_init_kernel(long long *sched, long long n_chains) {
+    SchedView Q(sched, n_chains);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < Q.cap; i += (long long)gridDim.x * blockDim.x) {
+        Q.ring[i] = i < n_chains ? ((1ull << 32) | (unsigned long long)i) : 0ull;
+        if (i < n_chains) Q.progress[i] = 0;
+        if (i == 0) {
+            *Q.head = 0;
+            *Q.tail = (unsigned long long)n_chains;
+        }
+    }
+}
+
+// Spin until lane 0 reads a value accepted by `ok` from *p; returns it on every lane.  The loop
+// condition is warp-uniform (lane 0 only issues a predicated load): a lane spinning on its own
+// does not reconverge with the other 31, and the whole solve would then run twice, once per part
+// of the split warp (measured: 4x slower).
+template <class OK>
+__device__ __forceinline__ unsigned long long spin_until(const unsigned long long *p, int lane, OK ok) {
+    while (true) {
+        unsigned long long v = 0;
+        if (lane == 0) v = ld_acquire_u64(p);
+        v = __shfl_sync(FULL, v, 0);
+        if (ok(v)) return v;
+        __nanosleep(64);
+    }
+}
+
+// MINB: 1 = one CTA per SM may use the whole register file (small batches: ptxas then schedules the
+// time-step loop without register pressure, ~400 instead of ~570 static stall cycles per step);
+// 2 = 128 registers, 16 warps per SM (large batches).
+template <int CPL, int NUMERICS, bool PADDED, int MINB>
+__global__ void __launch_bounds__(256, MINB) burgers_chain_queue_kernel(
+    const __grid_constant__ BurgersDev B, const __grid_constant__ SamplerDev S, const __grid_constant__ ChainBufDev C,
+    long long n_chains, long long n_steps, int chunk) {
+    extern __shared__ double smem_all[];
+    const int warp = threadIdx.x >> 5;
+    double *smem = smem_all + (size_t)warp * (B.N + 2 * IPMCMC_MAX_OBS);
+    double *state = smem, *Gs = smem + B.N, *r2 = Gs + IPMCMC_MAX_OBS;
+    const int lane = lane_id();
+    const Group Gp{0, 32, lane, FULL};
+    const int d = S.d;
+    SchedView Q(C.sched, n_chains);
+    const unsigned long long cap = (unsigned long long)Q.cap;
+    const long long items_per_chain = (n_steps + chunk - 1) / chunk;
+    const unsigned long long total = (unsigned long long)n_chains * (unsigned long long)items_per_chain;
+    while (true) {
+        // ---- take a ticket, wait for its ring slot to be filled, consume it
+        unsigned long long idx = 0;
+        if (lane == 0) idx = atomicAdd(Q.head, 1ull);
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx >= total) break;
+        unsigned long long *slot = Q.ring + idx % cap;
+        const unsigned long long want = idx / cap + 1;
+        const unsigned long long e = spin_until(slot, lane, [want](unsigned long long v) { return (v >> 32) == want; });
+        if (lane == 0) st_release_u64(slot, 0ull);
+        __syncwarp();
+        const long long c = (long long)(e & 0xffffffffull), cg = S.chain_offset + c;
+        // ---- chain state from L2 (another SM may have written it: bypass L1)
+        const long long s0 = __ldcg(Q.progress + c);
+        ChainRegs R;
+        R.ui = (lane < d) ? __ldcg(C.u + c * d + lane) : 0.0;
+        R.phi_u = __ldcg(C.phi + c);
+#pragma unroll
+        for (int k = 0; k < CNT_N; ++k) R.cnt[k] = 0;
+        if (isnan(R.phi_u)) {  // first launch: Phi(u_0) not known yet
+            int n_fv;
+            R.phi_u = burgers_phi<CPL, NUMERICS, PADDED>(B, R.ui, state, Gs, r2, lane, n_fv);
+            R.cnt[CNT_WORK_A] += n_fv;
+            R.cnt[CNT_WORK_B] += 1;
+        }
+        R.reg_u = (S.accepter == IPMCMC_ACCEPT_RW) ? prior_regulariser(S, Gp, R.ui) : 0.0;
+        R.mom = Welford{__ldcg(C.mom_count + c), (lane < d) ? __ldcg(C.mom_mean + c * d + lane) : 0.0,
+                        (lane < d) ? __ldcg(C.mom_m2 + c * d + lane) : 0.0};
+        const long long s1 = (s0 + chunk < n_steps) ? s0 + chunk : n_steps;
+        for (long long s = s0; s < s1; ++s)
+            burgers_metropolis_step<CPL, NUMERICS, PADDED>(B, S, C, Gp, c, cg, s, n_steps, state, Gs, r2, R);
+        // ---- write back, then hand the chain to the next free warp
+        if (lane < d) {
+            __stcg(C.u + c * d + lane, R.ui);
+            __stcg(C.mom_mean + c * d + lane, R.mom.mean);
+            __stcg(C.mom_m2 + c * d + lane, R.mom.m2);
+        }
+        if (lane == 0) {
+            __stcg(C.phi + c, R.phi_u);
+            __stcg(C.mom_count + c, R.mom.count);
+#pragma unroll
+            for (int k = 0; k < CNT_N; ++k) atomicAdd((unsigned long long *)(C.counters + c * CNT_N + k), (unsigned long long)R.cnt[k]);
+            __stcg(Q.progress + c, s1);
+        }
+        __threadfence();
+        __syncwarp();
+        if (s1 < n_steps) {   // warp-uniform
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd(Q.tail, 1ull);
+            t = __shfl_sync(FULL, t, 0);
+            unsigned long long *pslot = Q.ring + t % cap;
+            spin_until(pslot, lane, [](unsigned long long v) { return v == 0ull; });   // previous lap consumed (cap = 2n: no wait in practice)
+            if (lane == 0) st_release_u64(pslot, ((t / cap + 1) << 32) | (unsigned long long)c);
         }
         __syncwarp();
     }

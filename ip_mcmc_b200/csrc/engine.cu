@@ -216,6 +216,45 @@ static int burgers_launch_chain(ipmcmc_problem *p, const SamplerDev &S, const Ch
     return 0;
 }
 
+// Dynamic step scheduler (burgers_chain_queue_kernel): persistent warps, one wave.
+template <int CPL, int NUM, bool PAD>
+static int burgers_launch_chain_queue(ipmcmc_problem *p, const SamplerDev &S, const ChainBufDev &C, long long n_chains,
+                                      long long n_steps, int chunk, cudaStream_t st) {
+    int dev = 0, n_sm = 148;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    // small batches: one CTA of W = ceil(n / n_SM) warps per SM (warp w -> sub-partition w % 4);
+    // large batches: as many 4-warp CTAs as are resident at once (register and shared-memory limits)
+    int wpc, grid;
+    const bool small = n_chains <= 8LL * n_sm;
+    auto kern = small ? burgers_chain_queue_kernel<CPL, NUM, PAD, 1> : burgers_chain_queue_kernel<CPL, NUM, PAD, 2>;
+    if (small) {
+        wpc = (int)((n_chains + n_sm - 1) / n_sm);
+        if (const char *e = getenv("IPMCMC_SCHED_WPC")) wpc = atoi(e) > 0 && atoi(e) <= 8 ? atoi(e) : wpc;  // experiments
+        grid = (int)((n_chains + wpc - 1) / wpc);
+        if (grid > n_sm) grid = n_sm;
+        if (grid < n_sm && (long long)grid * wpc < n_chains) grid = n_sm;
+    } else {
+        wpc = 4;
+        grid = 0;
+    }
+    const size_t smem = burgers_smem_bytes(p->b.N, wpc);
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (grid == 0) {
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * wpc, smem));
+        if (per_sm < 1) per_sm = 1;
+        grid = per_sm * n_sm;
+        const long long need = (n_chains + wpc - 1) / wpc;
+        if (grid > need) grid = (int)need;
+    }
+    sched_init_kernel<<<(unsigned)((2 * n_chains + 255) / 256 < 1184 ? (2 * n_chains + 255) / 256 : 1184), 256, 0, st>>>(C.sched, n_chains);
+    CUDA_TRY(cudaGetLastError());
+    kern<<<grid, 32 * wpc, smem, st>>>(p->b, S, C, n_chains, n_steps, chunk);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 template <int NUM, int TM>
 static int burgers_launch_team_forward(ipmcmc_problem *p, long long n, const double *u, double *G, double *phi,
                                        double *state, long long *work, cudaStream_t st) {
@@ -401,11 +440,21 @@ extern "C" int ipmcmc_run(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, const
     C.inject_u = b->inject_u_dev;
     C.slot_chain = b->slot_chain_dev;
     C.n_slots = b->n_slots;
+    C.sched = nullptr;
     if (p->model == IPMCMC_MODEL_BURGERS) {
         int wpc = b->warps_per_cta > 0 ? b->warps_per_cta : 4;
         if (wpc > 8) return fail(IPMCMC_EINVAL, "warps_per_cta=%d > 8", wpc);
         if (b->slot_chain_dev && b->n_slots < 1) return fail(IPMCMC_EINVAL, "slot_chain_dev without n_slots");
         if (p->b.N > 1024) BURGERS_TEAM_DISPATCH(burgers_launch_team_chain, p, S, C, n_chains, n_steps, st);
+        if (b->sched_dev) {
+            if (b->sched_len < sched_len(n_chains))
+                return fail(IPMCMC_EINVAL, "sched_len=%lld < 3*n_chains+2", (long long)b->sched_len);
+            if (n_chains >= (1LL << 31)) return fail(IPMCMC_EUNSUPPORTED, "dynamic scheduler: n_chains >= 2^31");
+            int chunk = b->sched_chunk > 0 ? b->sched_chunk : 1;
+            if (const char *e = getenv("IPMCMC_SCHED_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;  // experiments
+            C.sched = (long long *)b->sched_dev;
+            BURGERS_DISPATCH(burgers_launch_chain_queue, p, S, C, n_chains, n_steps, chunk, st);
+        }
         BURGERS_DISPATCH(burgers_launch_chain, p, S, C, n_chains, n_steps, wpc, st);
     }
     const int groups = lorenz_groups(p->l.K);

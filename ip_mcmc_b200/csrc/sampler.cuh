@@ -37,6 +37,7 @@ struct ChainBufDev {
     const double *inject_w, *inject_u;
     const int *slot_chain;
     int n_slots;
+    long long *sched;   // dynamic step scheduler scratch (int64 [3*n_chains + 2]) or nullptr
 };
 
 enum : int { CNT_CALLS = 0, CNT_ACCEPTS, CNT_WORK_A, CNT_WORK_B, CNT_NONFINITE, CNT_CONSTRAINT, CNT_N };

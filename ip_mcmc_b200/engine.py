@@ -5,6 +5,7 @@ There is no CPU path: constructing a Problem without a CUDA device or without th
 raises.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -172,8 +173,9 @@ class ChainBatch:
 
     COUNTER_NAMES = ("calls", "accepts", "work_a", "work_b", "nonfinite", "constraint_rejects")
 
-    def __init__(self, problem, u0, n_chains=None, model_state=None, chain_offset=0):
+    def __init__(self, problem, u0, n_chains=None, model_state=None, chain_offset=0, scheduler=None):
         self.problem = problem
+        scheduler = scheduler or os.environ.get("IPMCMC_SCHEDULER", "dynamic")
         dev = problem.device
         d = problem.d
         u0 = np.asarray(u0, dtype=np.float64) if not torch.is_tensor(u0) else u0
@@ -215,9 +217,16 @@ class ChainBatch:
         self.launches = 0
         self.placement = None
         self._work_prev = None
+        self.sched = None          # scratch of the dynamic step scheduler (Burgers, N <= 1024)
+        self.sched_chunk = 1
         if problem.kind == _lib.MODEL_BURGERS:
             n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-            self.placement = Placement(self.n, n_sm, dev)
+            if scheduler == "dynamic" and problem.model.N <= 1024:
+                self.sched = torch.empty((3 * self.n + 2,), dtype=torch.int64, device=dev)
+            elif scheduler not in ("dynamic", "static"):
+                raise ValueError("scheduler must be 'dynamic' or 'static'")
+            else:
+                self.placement = Placement(self.n, n_sm, dev)
 
     def run(self, spec, n_steps, trace=None, steplog=None, vlog=None, inject_w=None, inject_u=None):
         """Advance all chains by n_steps in ONE launch of the fused kernel (ipmcmc_run).
@@ -238,6 +247,10 @@ class ChainBatch:
         b.vlog_dev = _ptr(vlog)
         b.inject_w_dev = _ptr(inject_w)
         b.inject_u_dev = _ptr(inject_u)
+        if self.sched is not None:
+            b.sched_dev = _ptr(self.sched)
+            b.sched_len = self.sched.numel()
+            b.sched_chunk = self.sched_chunk
         pl = self.placement
         if pl is not None:
             b.warps_per_cta = pl.W

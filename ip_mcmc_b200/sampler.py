@@ -56,7 +56,7 @@ class MCMCSampler:
         return spec, pot, a
 
     def run(self, u_0, n_samples, burn_in=1000, sample_interval=200, n_chains=None, chain_offset=0,
-            steps_per_launch=None, return_device=False, recompute_phi_u=None):
+            steps_per_launch=None, return_device=False, recompute_phi_u=None, scheduler=None):
         """Same step accounting as the reference (sampler.py:18-28): max(0, burn_in - interval)
         unrecorded steps, then n_samples * interval steps recording every interval-th state.
 
@@ -72,7 +72,7 @@ class MCMCSampler:
             self.accepter.reset()                   # only when outermost (sampler.py:15-16)
         problem = pot.problem()
         single = n_chains is None and np.ndim(u_0) == 1
-        chains = ChainBatch(problem, u_0, n_chains=n_chains, chain_offset=chain_offset)
+        chains = ChainBatch(problem, u_0, n_chains=n_chains, chain_offset=chain_offset, scheduler=scheduler)
         trace = torch.empty((chains.n, n_samples, chains.d), dtype=F64, device=problem.device)
         if steps_per_launch is None or steps_per_launch >= total:
             chains.run(spec, total, trace=trace)

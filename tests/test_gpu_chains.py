@@ -235,12 +235,33 @@ def test_placement_does_not_change_results(G):
     n = 5 * n_sm + 3                      # W = 6 warps per CTA -> placement active
     mk = lambda: M.MCMCSampler(M.ConstSteppCNProposer(0.25, prior), M.pCNAccepter(pot), np.random.default_rng(8))
     a = mk()
-    out_a = a.run(np.zeros(3), 12, 0, 1, n_chains=n, steps_per_launch=4)      # 3 launches: table used from the 2nd
+    out_a = a.run(np.zeros(3), 12, 0, 1, n_chains=n, steps_per_launch=4, scheduler="static")   # 3 launches: table used from the 2nd
     assert a.last_run["chains"].placement.active
     b = mk()
-    out_b = b.run(np.zeros(3), 12, 0, 1, n_chains=9 * n_sm)                   # > 8 n_SM: no placement
+    out_b = b.run(np.zeros(3), 12, 0, 1, n_chains=9 * n_sm, scheduler="static")                # > 8 n_SM: no placement
     assert not b.last_run["chains"].placement.active
     assert np.array_equal(out_a, out_b[:n])
+
+
+@pytest.mark.parametrize("N,n_chains,steps_per_launch", [(32, 700, None), (64, 1500, 5), (256, 1024, 7), (100, 333, 3)])
+def test_dynamic_scheduler_bit_identical_to_static(G, N, n_chains, steps_per_launch):
+    """The dynamic step scheduler (persistent warps + FIFO of ready chains, chain state travelling
+    through L2 between work items) is pure scheduling: samples, per-chain counters and Welford
+    moments equal the static one-chain-per-warp kernel bit for bit (small batch, > 8 n_SM batch,
+    the bench shape, a padded grid)."""
+    import ip_mcmc_b200 as M
+    f, pot, prior, _ = G.burgers_setup(N, "fused")
+    mk = lambda: M.MCMCSampler(M.ConstSteppCNProposer(0.25, prior), M.CountedAccepter(M.pCNAccepter(pot)),
+                               np.random.default_rng(8))
+    a, b = mk(), mk()
+    out_a = a.run(np.zeros(3), 10, 4, 2, n_chains=n_chains, steps_per_launch=steps_per_launch, scheduler="static")
+    out_b = b.run(np.zeros(3), 10, 4, 2, n_chains=n_chains, steps_per_launch=steps_per_launch, scheduler="dynamic")
+    ca, cb = a.last_run["chains"], b.last_run["chains"]
+    assert ca.sched is None and cb.sched is not None
+    assert np.array_equal(out_a, out_b)
+    assert torch.equal(ca.counters, cb.counters) and torch.equal(ca.u, cb.u) and torch.equal(ca.phi, cb.phi)
+    assert torch.equal(ca.mom_count, cb.mom_count) and torch.equal(ca.mom_mean, cb.mom_mean) and torch.equal(ca.mom_m2, cb.mom_m2)
+    assert a.accepter.calls == b.accepter.calls and a.accepter.accepts == b.accepter.accepts
 
 
 def test_grid_refinement_study_driver(G):

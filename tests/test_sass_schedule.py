@@ -1,0 +1,57 @@
+"""Build-time guard (no GPU needed): ptxas' schedule of the Burgers time-step loop is sensitive to
+unrelated edits (register pressure at the call site of the solver decides whether the second SSPRK2
+stage is interleaved or serialised: ~390 vs ~570 static stall cycles per time step, a 15-20 %
+throughput difference measured on B200).  The bench kernels must keep the good schedule."""
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def _main_loop(sass_path, kernel_regex):
+    from sass_loops import functions
+    from sass_loop import parse
+    import tempfile
+    best = None
+    for name, body in functions(sass_path):
+        if not re.search(kernel_regex, name):
+            continue
+        with tempfile.NamedTemporaryFile("w", suffix=".sass", delete=False) as f:
+            f.write(body)
+        ins = parse(f.name)
+        os.unlink(f.name)
+        by_addr = {x["addr"]: k for k, x in enumerate(ins)}
+        for k, x in enumerate(ins):
+            m = re.search(r"BRA\S*\s+(?:\w+,\s*)*(0x[0-9a-f]+)", x["text"])
+            if not m:
+                continue
+            tgt = int(m.group(1), 16)
+            if tgt < x["addr"] and tgt in by_addr:
+                loop = ins[by_addr[tgt]:k + 1]
+                f64 = sum(1 for y in loop if re.search(r"\b(DADD|DMUL|DFMA|DSETP)\b", y["text"]))
+                if len(loop) < 400 and f64 >= 120 and (best is None or len(loop) < best[0]):
+                    best = (len(loop), f64, sum(max(1, y["stall"]) for y in loop))
+    return best
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+def test_bench_kernel_time_step_loop_schedule(tmp_path):
+    from ip_mcmc_b200 import build
+    lib = build.build()
+    sass = tmp_path / "lib.sass"
+    # the 1024 x 256 bench shape: CPL = 8, FUSED numerics, dynamic scheduler, one CTA per SM
+    fun = "_ZN6ipmcmc26burgers_chain_queue_kernelILi8ELi1ELb0ELi1EEEvNS_10BurgersDevENS_10SamplerDevENS_11ChainBufDevExxi"
+    with open(sass, "w") as f:
+        subprocess.run(["cuobjdump", "-sass", "-fun", fun, lib], stdout=f, stderr=subprocess.DEVNULL, check=False)
+    got = _main_loop(str(sass), "burgers_chain_queue_kernelILi8ELi1ELb0ELi1E")
+    assert got is not None, "time-step loop of the bench kernel not found in the SASS"
+    n_ins, n_f64, stalls = got
+    assert n_f64 <= 135, "fp64 instructions per 256-cell time step grew: %d" % n_f64
+    assert stalls <= 450, ("ptxas serialised the time-step loop (static stall sum %d > 450): "
+                           "see tools/sass_loops.py and DESIGN.md section 4.1" % stalls)
