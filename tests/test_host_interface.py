@@ -43,7 +43,7 @@ def test_ctypes_struct_layout_matches_header_sizes():
     assert ctypes.sizeof(_lib.BurgersDesc) == 16 + 24 + 32 + 16 + 48
     assert ctypes.sizeof(_lib.LorenzDesc) == 16 + 32 + 8 + 48
     assert ctypes.sizeof(_lib.SamplerDesc) == 32 + 16 + 16 + 40 + 40
-    assert ctypes.sizeof(_lib.ChainBuffers) == 15 * 8
+    assert ctypes.sizeof(_lib.ChainBuffers) == 18 * 8
 
 
 def test_argument_validation_without_gpu():
