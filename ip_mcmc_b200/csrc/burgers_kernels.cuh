@@ -17,6 +17,20 @@
 
 namespace ipmcmc {
 
+// Developer instrumentation (-DIPMCMC_PROF=1, tools/overhead_probe.py): cycles per section of a work
+// item, summed over all warps by lane 0.  Not compiled into the product library.
+#ifndef IPMCMC_PROF
+#define IPMCMC_PROF 0
+#endif
+#if IPMCMC_PROF
+__device__ unsigned long long g_prof[16];
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(slot, a, b) do { if (lane_id() == 0) atomicAdd(&g_prof[slot], (unsigned long long)((b) - (a))); } while (0)
+#else
+#define PROF_T(var)
+#define PROF_ADD(slot, a, b)
+#endif
+
 // shared memory layout per warp: state[N] | G[MAX_OBS] | r2[MAX_OBS]
 __host__ __device__ inline size_t burgers_smem_bytes(int N, int warps = 1) {
     return (size_t)warps * (N + 2 * IPMCMC_MAX_OBS) * sizeof(double);
@@ -46,7 +60,9 @@ __device__ __noinline__ double burgers_phi(const BurgersDev &B, double ui, doubl
     // FVMObservationOperator.__call__ (utilities.py:40-41): IC(u_0 + u)
     const double pi = (lane < B.d) ? B.param_mean[lane] + ui : 0.0;
     BurgersWarp<CPL, NUMERICS, PADDED> W;
+    PROF_T(p0);
     n_fv = W.integrate(B, pi, lane);
+    PROF_T(p1);
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
         const int c = lane * CPL + k;
@@ -55,6 +71,9 @@ __device__ __noinline__ double burgers_phi(const BurgersDev &B, double ui, doubl
     __syncwarp();
     burgers_measure(B, state, Gs, lane);
     const double phi = potential_from_G(B.pot, Gs, r2, lane, 32, FULL);
+    PROF_T(p2);
+    PROF_ADD(3, p0, p1);
+    PROF_ADD(4, p1, p2);
     // a solve stopped by the safety cap has not reached T: report it as non-finite (-> rejected)
     return W.capped ? nan("") : phi;
 }
@@ -98,22 +117,33 @@ struct ChainRegs {
 // Number of recorded steps in [record_start, g): recorded are the g with (g - record_start + 1) % interval == 0
 // (sampler.py:23-28).
 __device__ __forceinline__ long long recorded_before(const SamplerDev &S, long long g) {
-    return (S.record_interval > 0 && g > S.record_start) ? (g - S.record_start) / S.record_interval : 0;
+    if (!(S.record_interval > 0 && g > S.record_start)) return 0;
+    return (g - S.record_start) / S.record_interval;
+}
+__device__ __forceinline__ bool records_step(const SamplerDev &S, long long gstep) {
+    if (!(S.record_interval > 0 && gstep >= S.record_start)) return false;
+    return ((gstep - S.record_start + 1) % S.record_interval) == 0;
 }
 
 // ONE Metropolis step of chain c (local id; cg global id) at launch-local step s: proposal -> (box
 // constraint) -> solve -> Phi(v) -> accept/reject -> counters, logs, moments, trace.
+#ifndef IPMCMC_STEP_INLINE
+#define IPMCMC_STEP_INLINE __forceinline__
+#endif
 template <int CPL, int NUMERICS, bool PADDED>
-__device__ __forceinline__ void burgers_metropolis_step(const BurgersDev &B, const SamplerDev &S, const ChainBufDev &C,
+__device__ IPMCMC_STEP_INLINE void burgers_metropolis_step(const BurgersDev &B, const SamplerDev &S, const ChainBufDev &C,
                                                         const Group &Gp, long long c, long long cg, long long s,
                                                         long long n_steps, double *state, double *Gs, double *r2,
                                                         ChainRegs &R) {
     const int lane = Gp.lane, d = S.d;
     const long long gstep = S.first_step + s;
     double ca, cb;
+    PROF_T(q0);
     step_coefs(S, gstep, ca, cb);
     const double w = proposal_noise(S, C, Gp, c, cg, s, n_steps, gstep);
     const double vi = ca * R.ui + cb * w;
+    PROF_T(q1);
+    PROF_ADD(2, q0, q1);
     if (C.vlog && lane < d) C.vlog[(c * n_steps + s) * d + lane] = vi;
     bool accepted = false;
     double phi_v = nan(""), a = nan("");
@@ -127,6 +157,7 @@ __device__ __forceinline__ void burgers_metropolis_step(const BurgersDev &B, con
             R.cnt[CNT_WORK_B] += 1;
         }
         phi_v = burgers_phi<CPL, NUMERICS, PADDED>(B, vi, state, Gs, r2, lane, n_fv);
+        PROF_T(q2);
         R.cnt[CNT_WORK_A] += n_fv;
         R.cnt[CNT_WORK_B] += 1;
         double reg_v = 0.0;
@@ -140,6 +171,8 @@ __device__ __forceinline__ void burgers_metropolis_step(const BurgersDev &B, con
             R.phi_u = phi_v;
             R.reg_u = reg_v;
         }
+        PROF_T(q3);
+        PROF_ADD(5, q2, q3);
     } else {
         R.cnt[CNT_CONSTRAINT] += 1;
     }
@@ -153,7 +186,7 @@ __device__ __forceinline__ void burgers_metropolis_step(const BurgersDev &B, con
         L[3] = (double)n_fv;
     }
     // recording (sampler.py:23-28)
-    if (S.record_interval > 0 && gstep >= S.record_start && ((gstep - S.record_start + 1) % S.record_interval) == 0) {
+    if (records_step(S, gstep)) {
         R.mom.add(R.ui);
         const long long n_rec = recorded_before(S, gstep) - recorded_before(S, S.first_step);
         if (C.trace && n_rec < C.n_record && lane < d) C.trace[(c * C.n_record + n_rec) * d + lane] = R.ui;
@@ -243,6 +276,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 __global__ void sched_init_kernel(long long *sched, long long n_chains) {
     SchedView Q(sched, n_chains);
@@ -291,6 +327,7 @@ __global__ void __launch_bounds__(256, MINB) burgers_chain_queue_kernel(
     const unsigned long long total = (unsigned long long)n_chains * (unsigned long long)items_per_chain;
     while (true) {
         // ---- take a ticket, wait for its ring slot to be filled, consume it
+        PROF_T(t0);
         unsigned long long idx = 0;
         if (lane == 0) idx = atomicAdd(Q.head, 1ull);
         idx = __shfl_sync(FULL, idx, 0);
@@ -298,7 +335,8 @@ __global__ void __launch_bounds__(256, MINB) burgers_chain_queue_kernel(
         unsigned long long *slot = Q.ring + idx % cap;
         const unsigned long long want = idx / cap + 1;
         const unsigned long long e = spin_until(slot, lane, [want](unsigned long long v) { return (v >> 32) == want; });
-        if (lane == 0) st_release_u64(slot, 0ull);
+        // mark the slot consumed: ordered after our own read of it (same address), nothing to publish
+        if (lane == 0) st_relaxed_u64(slot, 0ull);
         __syncwarp();
         const long long c = (long long)(e & 0xffffffffull), cg = S.chain_offset + c;
         // ---- chain state from L2 (another SM may have written it: bypass L1)
@@ -318,9 +356,13 @@ __global__ void __launch_bounds__(256, MINB) burgers_chain_queue_kernel(
         R.mom = Welford{__ldcg(C.mom_count + c), (lane < d) ? __ldcg(C.mom_mean + c * d + lane) : 0.0,
                         (lane < d) ? __ldcg(C.mom_m2 + c * d + lane) : 0.0};
         const long long s1 = (s0 + chunk < n_steps) ? s0 + chunk : n_steps;
+        PROF_T(t1);
         for (long long s = s0; s < s1; ++s)
             burgers_metropolis_step<CPL, NUMERICS, PADDED>(B, S, C, Gp, c, cg, s, n_steps, state, Gs, r2, R);
-        // ---- write back, then hand the chain to the next free warp
+        PROF_T(t2);
+        // ---- write back, then hand the chain to the next free warp.  The chain state is published by
+        // the release store of the ring entry (no separate fence): the other lanes' stores are ordered
+        // before it by __syncwarp (cumulativity).
         if (lane < d) {
             __stcg(C.u + c * d + lane, R.ui);
             __stcg(C.mom_mean + c * d + lane, R.mom.mean);
@@ -333,7 +375,6 @@ __global__ void __launch_bounds__(256, MINB) burgers_chain_queue_kernel(
             for (int k = 0; k < CNT_N; ++k) atomicAdd((unsigned long long *)(C.counters + c * CNT_N + k), (unsigned long long)R.cnt[k]);
             __stcg(Q.progress + c, s1);
         }
-        __threadfence();
         __syncwarp();
         if (s1 < n_steps) {   // warp-uniform
             unsigned long long t = 0;
@@ -344,6 +385,12 @@ __global__ void __launch_bounds__(256, MINB) burgers_chain_queue_kernel(
             if (lane == 0) st_release_u64(pslot, ((t / cap + 1) << 32) | (unsigned long long)c);
         }
         __syncwarp();
+        PROF_T(t3);
+        PROF_ADD(0, t0, t3);
+        PROF_ADD(1, t0, t1);
+        PROF_ADD(6, t1, t2);
+        PROF_ADD(7, t2, t3);
+        PROF_ADD(8, 0, 1);
     }
 }
 
@@ -478,8 +525,7 @@ __global__ void __launch_bounds__(32 * TM) burgers_team_chain_kernel(const __gri
                 L[2] = accepted ? 1.0 : 0.0;
                 L[3] = (double)n_fv;
             }
-            if (S.record_interval > 0 && gstep >= S.record_start &&
-                ((gstep - S.record_start + 1) % S.record_interval) == 0) {
+            if (records_step(S, gstep)) {
                 mom.add(ui);
                 if (writer && C.trace && n_rec < C.n_record && lane < d)
                     C.trace[(c * C.n_record + n_rec) * d + lane] = ui;

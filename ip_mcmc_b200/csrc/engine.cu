@@ -659,3 +659,16 @@ extern "C" int ipmcmc_fp64_peak(int32_t iters, double *tflops_out) {
     *tflops_out = best;
     return 0;
 }
+
+#if IPMCMC_PROF
+// developer instrumentation only (tools/overhead_probe.py); not declared in include/ipmcmc.h
+extern "C" int ipmcmc_prof_read(unsigned long long *out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, ipmcmc::g_prof, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(ipmcmc::g_prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif

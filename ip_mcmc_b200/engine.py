@@ -218,7 +218,7 @@ class ChainBatch:
         self.placement = None
         self._work_prev = None
         self.sched = None          # scratch of the dynamic step scheduler (Burgers, N <= 1024)
-        self.sched_chunk = 1
+        self.sched_chunk = 0       # Metropolis steps per work item; 0 = min(4, max(1, n_steps // 64)) per launch
         if problem.kind == _lib.MODEL_BURGERS:
             n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
             if scheduler == "dynamic" and problem.model.N <= 1024:
@@ -250,7 +250,9 @@ class ChainBatch:
         if self.sched is not None:
             b.sched_dev = _ptr(self.sched)
             b.sched_len = self.sched.numel()
-            b.sched_chunk = self.sched_chunk
+            # a work item costs ~4 us of queue traffic and state reloads: long launches use longer
+            # items (measured on B200, 1024 x 256 cells: +1 % at 200 steps per launch; 50 steps: none)
+            b.sched_chunk = self.sched_chunk or min(4, max(1, int(n_steps) // 64))
         pl = self.placement
         if pl is not None:
             b.warps_per_cta = pl.W

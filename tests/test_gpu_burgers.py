@@ -43,6 +43,36 @@ def test_forward_fused_within_tolerance(G, N):
     np.testing.assert_allclose(r["state"].cpu().numpy(), g["end_state"], rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("N", [33, 64, 128, 224, 256, 512, 1024])
+def test_forward_fused_positive_and_sign_changing_states(G, N):
+    """FUSED runs a select-free time loop when the initial data are positive everywhere and the general
+    (upwind-select) loop otherwise (burgers.cuh, flux_fused<.., POS>); both must agree with the
+    reference-order solver to the north-star tolerance, on padded and unpadded layouts, for the rotated
+    loop (<= 8 cells per lane) and the plain one."""
+    P = B.BurgersProblem(N)
+    pm = P.prior_mean
+    params = np.array([
+        [0.025, 0.225, -0.02],     # left 1.025 / right 0.225: positive everywhere
+        [1.5, 0.5, 0.3],           # left 2.5 / right 0.5: positive, strong shock
+        [0.025, -0.025, -0.02],    # the reference's truth: right state negative (general loop)
+        [-0.4, -0.3, 0.1],         # left 0.6 / right -0.3
+        [-1.5, 0.4, -0.2],         # left -0.5 / right 0.4: rarefaction through u = 0
+        [0.1, 1e-12, 0.0],         # right state barely positive
+        [0.1, 0.0, 0.0],           # right state exactly zero (not > 0: general loop)
+    ])
+    u = params - pm
+    fe, pe, _, y = G.burgers_setup(N, "exact")
+    ff, pf, _, _ = G.burgers_setup(N, "fused", y=y)
+    re_ = pe.problem().forward(u, want_state=True)
+    rf = pf.problem().forward(u, want_state=True)
+    for i in range(len(u)):
+        assert np.array_equal(re_["state"][i].cpu().numpy(), P.end_state(pm + u[i])), (N, i)
+    np.testing.assert_array_equal(rf["work"].cpu().numpy()[:, 0], re_["work"].cpu().numpy()[:, 0])
+    np.testing.assert_allclose(rf["state"].cpu().numpy(), re_["state"].cpu().numpy(), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(rf["G"].cpu().numpy(), re_["G"].cpu().numpy(), rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(rf["phi"].cpu().numpy(), re_["phi"].cpu().numpy(), rtol=RTOL)
+
+
 @pytest.mark.parametrize("N", [16, 33, 48, 64, 96, 224, 255, 512])
 def test_forward_random_parameters_vs_oracle(G, N):
     """Grids the fixtures do not cover (padded layouts, every CPL instantiation), random u drawn

@@ -14,11 +14,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
-def _main_loop(sass_path, kernel_regex):
+def _time_step_loops(sass_path, kernel_regex):
+    """(instructions, fp64 instructions, static stall sum) of every time-step loop of the kernel."""
     from sass_loops import functions
     from sass_loop import parse
     import tempfile
-    best = None
+    found = []
     for name, body in functions(sass_path):
         if not re.search(kernel_regex, name):
             continue
@@ -35,9 +36,9 @@ def _main_loop(sass_path, kernel_regex):
             if tgt < x["addr"] and tgt in by_addr:
                 loop = ins[by_addr[tgt]:k + 1]
                 f64 = sum(1 for y in loop if re.search(r"\b(DADD|DMUL|DFMA|DSETP)\b", y["text"]))
-                if len(loop) < 400 and f64 >= 120 and (best is None or len(loop) < best[0]):
-                    best = (len(loop), f64, sum(max(1, y["stall"]) for y in loop))
-    return best
+                if len(loop) < 400 and f64 >= 100:
+                    found.append((len(loop), f64, sum(max(1, y["stall"]) for y in loop)))
+    return found
 
 
 @pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
@@ -49,9 +50,12 @@ def test_bench_kernel_time_step_loop_schedule(tmp_path):
     fun = "_ZN6ipmcmc26burgers_chain_queue_kernelILi8ELi1ELb0ELi1EEEvNS_10BurgersDevENS_10SamplerDevENS_11ChainBufDevExxi"
     with open(sass, "w") as f:
         subprocess.run(["cuobjdump", "-sass", "-fun", fun, lib], stdout=f, stderr=subprocess.DEVNULL, check=False)
-    got = _main_loop(str(sass), "burgers_chain_queue_kernelILi8ELi1ELb0ELi1E")
-    assert got is not None, "time-step loop of the bench kernel not found in the SASS"
-    n_ins, n_f64, stalls = got
-    assert n_f64 <= 135, "fp64 instructions per 256-cell time step grew: %d" % n_f64
-    assert stalls <= 450, ("ptxas serialised the time-step loop (static stall sum %d > 450): "
-                           "see tools/sass_loops.py and DESIGN.md section 4.1" % stalls)
+    loops = _time_step_loops(str(sass), "burgers_chain_queue_kernelILi8ELi1ELb0ELi1E")
+    # two rotated time-step loops (burgers.cuh, time_loop_pipelined): the select-free one for positive
+    # states and the general one; both include the rarely taken ~50-instruction repair block
+    assert len(loops) == 2, "expected the positive-state and the general time-step loop, found %r" % (loops,)
+    pos, gen = sorted(loops, key=lambda t: t[1])
+    assert pos[1] <= 120 and gen[1] <= 140, "fp64 instructions per 256-cell time step grew: %r" % (loops,)
+    assert pos[2] <= 480 and gen[2] <= 540, (
+        "ptxas serialised a time-step loop (static stall sums %d / %d, limits 480 / 540): unrelated edits move "
+        "its register allocation; see tools/sass_loops.py and DESIGN.md section 4.1" % (pos[2], gen[2]))

@@ -49,6 +49,8 @@ __global__ void thr(double *out, long long *cyc, double a, double b, int n) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = a + threadIdx.x + k;
     uint32_t z = threadIdx.x;
+    double creg;
+    asm volatile("mov.f64 %0, %1;" : "=d"(creg) : "d"(a));
     long long t0 = clock64();
     for (int i = 0; i < n; ++i) {
 #pragma unroll
@@ -69,6 +71,12 @@ __global__ void thr(double *out, long long *cyc, double a, double b, int n) {
                 if (MIX == 11) x[k] = fma(x[k], a, x[(k + 1) & 7]);                     // DFMA const-bank operand + 2 regs
                 if (MIX == 12) { double t = x[k] + a; t = t + b; x[k] = (__double2hiint(x[(k + 1) & 7]) >= 0) ? t + a : x[(k + 2) & 7]; }  // 3 DADD + ISETP + 2 FSEL
                 if (MIX == 13) { double t = x[k] + a; t = t + b; t = t * a; x[k] = (__double2hiint(x[(k + 1) & 7]) >= 0) ? t + a : x[(k + 2) & 7]; }  // 4 fp64 + 3 ALU
+                if (MIX == 15) x[k] = fma(creg, x[(k + 1) & 7], x[k]);                  // DFMA, 3 registers, first shared by all (reuse cache)
+                if (MIX == 16) { x[k] = fma(creg, x[(k + 1) & 7], x[k]); x[k] = fma(x[k], 2.0, -x[(k + 2) & 7]); }  // 3-reg DFMA + imm DFMA
+                if (MIX == 17) { double t = x[k] + a; x[k] = (threadIdx.x & (1 << k)) ? t : x[(k + 2) & 7]; }  // 1 DADD + 2 FSEL (predicate hoisted)
+                if (MIX == 18) { double t = x[k] + a; t = t * b; x[k] = (threadIdx.x & (1 << k)) ? t : x[(k + 2) & 7]; }  // 2 fp64 + 2 FSEL
+                if (MIX == 19) { double t = x[k] + a; t = t * b; t = fma(t, -0.5, x[(k + 3) & 7]); x[k] = (threadIdx.x & (1 << k)) ? t : x[(k + 2) & 7]; }  // 3 fp64 + 2 FSEL
+                if (MIX == 20) { double t = x[k] + a; x[k] = (x[(k + 1) & 7] >= -t) ? t : x[(k + 2) & 7]; }  // DADD + DSETP + 2 FSEL
                 if (MIX == 14) { double t = x[k] + a; t = t + b; t = t * a; t = t + b; t = t * a; x[k] = (__double2hiint(x[(k + 1) & 7]) >= 0) ? t + a : x[(k + 2) & 7]; }  // 6 fp64 + 3 ALU
             }
         }
@@ -121,5 +129,11 @@ int main() {
     run_thr<12>("3 fp64 + 3 ALU (per group)");
     run_thr<13>("4 fp64 + 3 ALU (per group)");
     run_thr<14>("6 fp64 + 3 ALU (per group)");
+    run_thr<15>("DFMA 3 regs, one shared");
+    run_thr<16>("DFMA 3 regs shared + DFMA imm (/grp)");
+    run_thr<17>("1 DADD + 2 FSEL (per group)");
+    run_thr<18>("2 fp64 + 2 FSEL (per group)");
+    run_thr<19>("3 fp64 + 2 FSEL (per group)");
+    run_thr<20>("DADD + DSETP + 2 FSEL (per group)");
     return 0;
 }
