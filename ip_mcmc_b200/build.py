@@ -10,11 +10,21 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libipmcmc.so")
-SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "philox.cuh", "burgers.cuh", "burgers_kernels.cuh", "burgers_team.cuh", "lorenz.cuh",
-           "lorenz_kernels.cuh", "sampler.cuh", os.path.join("..", "..", "include", "ipmcmc.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",
-              "-std=c++17", "--extended-lambda", "--split-compile=0", "-shared", "-Xcompiler", "-fPIC"]
+OBJ = os.path.join(PKG, "_build")
+# Translation units: the C ABI + Lorenz + small kernels, and the Burgers kernels once per cells-per-lane
+# value (0 = the team kernels for 2048 / 4096 cells).  They compile in parallel, and an edit to one kernel
+# family cannot move ptxas' schedule of another.
+UNITS = [("engine", "engine.cu", [])] + [("burgers_cpl%d" % c, "burgers_inst.cu", ["-DIPMCMC_TU_CPL=%d" % c])
+                                         for c in (32, 16, 8, 7, 4, 2, 1, 0)]
+SOURCES = ["engine.cu", "burgers_inst.cu"]
+HEADERS = ["common.cuh", "philox.cuh", "burgers.cuh", "burgers_kernels.cuh", "burgers_team.cuh", "burgers_launch.cuh",
+           "burgers_launch_impl.cuh", "lorenz.cuh", "lorenz_kernels.cuh", "sampler.cuh",
+           os.path.join("..", "..", "include", "ipmcmc.h")]
+# No --split-compile: with it ptxas' output is not reproducible (the schedule of the Burgers time-step loop
+# came out in one of two variants, 15 % apart in throughput, from one build of the same source to the next).
+CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+          "--extended-lambda", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = CFLAGS      # (name kept for tools/)
 
 
 def _stale():
@@ -24,18 +34,38 @@ def _stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+def compile_units(out_lib, extra_flags=(), obj_dir=None, verbose=False):
+    """nvcc -c every translation unit (in parallel), then link them into out_lib."""
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = os.environ.get("NVCC", "nvcc")
+    obj_dir = obj_dir or OBJ
+    os.makedirs(obj_dir, exist_ok=True)
+
+    def one(unit):
+        name, src, defs = unit
+        obj = os.path.join(obj_dir, name + ".o")
+        cmd = [nvcc] + CFLAGS + list(extra_flags) + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr[-4000:]))
+        if verbose:
+            sys.stderr.write(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max(1, min(len(UNITS), os.cpu_count() or 1))) as ex:
+        objs = list(ex.map(one, UNITS))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out_lib] + objs
+    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (" ".join(cmd), r.stderr[-4000:]))
+    return out_lib
+
+
 def build(force=False, verbose=False):
     """Compile the library if it is missing or older than its sources. Returns the path."""
     if not force and not _stale():
         return LIB
-    nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr[-4000:]))
-    if verbose:
-        sys.stderr.write(r.stderr)
-    return LIB
+    return compile_units(LIB, verbose=verbose)
 
 
 if __name__ == "__main__":

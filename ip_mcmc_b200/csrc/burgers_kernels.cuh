@@ -7,12 +7,11 @@
 #include "burgers_team.cuh"
 #include "sampler.cuh"
 
+// Register budget of the static chain kernel: 128 registers (2 CTAs of 256 threads per SM) up to 8 cells
+// per lane, 255 from 16 cells per lane on, where 128 spill the state (measured: engine.cu,
+// burgers_launch_chain_queue).
 #ifndef IPMCMC_CHAIN_MINB
-#define IPMCMC_CHAIN_MINB 2   // register budget of the chain kernel: 2 -> 128, 1 -> 255 registers per thread
-#endif
-
-#ifndef IPMCMC_CHAIN_MINB
-#define IPMCMC_CHAIN_MINB 2   // register budget of the static chain kernel: 2 -> 128, 1 -> 255 registers per thread
+#define IPMCMC_CHAIN_MINB(CPL) ((CPL) >= 16 ? 1 : 2)
 #endif
 
 namespace ipmcmc {
@@ -23,7 +22,7 @@ namespace ipmcmc {
 #define IPMCMC_PROF 0
 #endif
 #if IPMCMC_PROF
-__device__ unsigned long long g_prof[16];
+static __device__ unsigned long long g_prof[16];
 #define PROF_T(var) const long long var = clock64()
 #define PROF_ADD(slot, a, b) do { if (lane_id() == 0) atomicAdd(&g_prof[slot], (unsigned long long)((b) - (a))); } while (0)
 #else
@@ -54,8 +53,14 @@ __device__ __forceinline__ void burgers_measure(const BurgersDev &B, const doubl
 
 // G(u) and Phi(u) for the parameter vector whose component i sits on lane i (value `ui`).
 // Leaves the end state in smem `state` and G in `Gs`.  Returns Phi; n_fv by reference.
+// Inlined at its call sites on purpose: with the solve as an out-of-line subroutine ptxas allocates the
+// time-step loop's registers around the call convention and schedules it measurably worse (B200,
+// 1024 x 256 cells: 60 % of the fp64 peak out of line, 66 % inlined; 8192 x 1024: 78 % / 83 %).
+#ifndef IPMCMC_PHI_INLINE
+#define IPMCMC_PHI_INLINE __forceinline__
+#endif
 template <int CPL, int NUMERICS, bool PADDED>
-__device__ __noinline__ double burgers_phi(const BurgersDev &B, double ui, double *state, double *Gs, double *r2,
+__device__ IPMCMC_PHI_INLINE double burgers_phi(const BurgersDev &B, double ui, double *state, double *Gs, double *r2,
                                               int lane, int &n_fv) {
     // FVMObservationOperator.__call__ (utilities.py:40-41): IC(u_0 + u)
     const double pi = (lane < B.d) ? B.param_mean[lane] + ui : 0.0;
@@ -196,7 +201,7 @@ __device__ IPMCMC_STEP_INLINE void burgers_metropolis_step(const BurgersDev &B, 
 // W warps per CTA, one chain per warp.  Warps never synchronise with each other; the CTA shape
 // only pins which chains share an SM sub-partition (warp w -> SMSP w % 4).
 template <int CPL, int NUMERICS, bool PADDED>
-__global__ void __launch_bounds__(256, IPMCMC_CHAIN_MINB) burgers_chain_kernel(const __grid_constant__ BurgersDev B,
+__global__ void __launch_bounds__(256, IPMCMC_CHAIN_MINB(CPL)) burgers_chain_kernel(const __grid_constant__ BurgersDev B,
                                                             const __grid_constant__ SamplerDev S,
                                                             const __grid_constant__ ChainBufDev C, long long n_chains,
                                                             long long n_steps) {
@@ -280,7 +285,7 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void sched_init_kernel(long long *sched, long long n_chains) {
+static __global__ void sched_init_kernel(long long *sched, long long n_chains) {
     SchedView Q(sched, n_chains);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < Q.cap; i += (long long)gridDim.x * blockDim.x) {
         Q.ring[i] = i < n_chains ? ((1ull << 32) | (unsigned long long)i) : 0ull;
@@ -307,9 +312,8 @@ __device__ __forceinline__ unsigned long long spin_until(const unsigned long lon
     }
 }
 
-// MINB: 1 = one CTA per SM may use the whole register file (small batches: ptxas then schedules the
-// time-step loop without register pressure, ~400 instead of ~570 static stall cycles per step);
-// 2 = 128 registers, 16 warps per SM (large batches).
+// MINB: register budget, 2 = 128 registers (16 warps per SM), 1 = 255 registers; chosen by the number of
+// cells per lane in burgers_launch_chain_queue (engine.cu), where the measurements are quoted.
 template <int CPL, int NUMERICS, bool PADDED, int MINB>
 __global__ void __launch_bounds__(256, MINB) burgers_chain_queue_kernel(
     const __grid_constant__ BurgersDev B, const __grid_constant__ SamplerDev S, const __grid_constant__ ChainBufDev C,

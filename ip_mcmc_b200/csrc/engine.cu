@@ -8,7 +8,7 @@
 #include <string>
 #include <vector>
 
-#include "burgers_kernels.cuh"
+#include "burgers_launch.cuh"
 #include "lorenz_kernels.cuh"
 
 using namespace ipmcmc;
@@ -190,102 +190,22 @@ extern "C" int ipmcmc_lorenz_create(const ipmcmc_lorenz_desc *d, ipmcmc_problem 
 // ------------------------------------------------------------------------------------------------
 static int grid_for(long long n_blocks) { return (int)(n_blocks < 2147483647LL ? n_blocks : 2147483647LL); }
 
-template <int CPL, int NUM, bool PAD>
-static int burgers_launch_forward(ipmcmc_problem *p, long long n, const double *u, double *G, double *phi,
-                                  double *state, long long *work, cudaStream_t st) {
-    // one chain per warp; CTAs of 4 warps (one per SM sub-partition) unless the batch is tiny
-    int wpc = n >= 4 * 148 ? 4 : 1;
-    if (const char *e = getenv("IPMCMC_FWD_WPC")) wpc = atoi(e) > 0 && atoi(e) <= 8 ? atoi(e) : wpc;  // experiments
-    const size_t smem = burgers_smem_bytes(p->b.N, wpc);
-    auto kern = burgers_forward_kernel<CPL, NUM, PAD>;
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid_for((n + wpc - 1) / wpc), 32 * wpc, smem, st>>>(p->b, n, u, G, phi, state, work);
-    CUDA_TRY(cudaGetLastError());
+static int cu(cudaError_t e) {
+    if (e != cudaSuccess) return fail(IPMCMC_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
     return 0;
 }
 
-template <int CPL, int NUM, bool PAD>
-static int burgers_launch_chain(ipmcmc_problem *p, const SamplerDev &S, const ChainBufDev &C, long long n_chains,
-                                long long n_steps, int wpc, cudaStream_t st) {
-    const size_t smem = burgers_smem_bytes(p->b.N, wpc);
-    auto kern = burgers_chain_kernel<CPL, NUM, PAD>;
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long slots = C.slot_chain ? (long long)C.n_slots : n_chains;
-    kern<<<grid_for((slots + wpc - 1) / wpc), 32 * wpc, smem, st>>>(p->b, S, C, n_chains, n_steps);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
-// Dynamic step scheduler (burgers_chain_queue_kernel): persistent warps, one wave.
-template <int CPL, int NUM, bool PAD>
-static int burgers_launch_chain_queue(ipmcmc_problem *p, const SamplerDev &S, const ChainBufDev &C, long long n_chains,
-                                      long long n_steps, int chunk, cudaStream_t st) {
-    int dev = 0, n_sm = 148;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    // small batches: one CTA of W = ceil(n / n_SM) warps per SM (warp w -> sub-partition w % 4);
-    // large batches: as many 4-warp CTAs as are resident at once (register and shared-memory limits)
-    int wpc, grid;
-    const bool small = n_chains <= 8LL * n_sm;
-    auto kern = small ? burgers_chain_queue_kernel<CPL, NUM, PAD, 1> : burgers_chain_queue_kernel<CPL, NUM, PAD, 2>;
-    if (small) {
-        wpc = (int)((n_chains + n_sm - 1) / n_sm);
-        if (const char *e = getenv("IPMCMC_SCHED_WPC")) wpc = atoi(e) > 0 && atoi(e) <= 8 ? atoi(e) : wpc;  // experiments
-        grid = (int)((n_chains + wpc - 1) / wpc);
-        if (grid > n_sm) grid = n_sm;
-        if (grid < n_sm && (long long)grid * wpc < n_chains) grid = n_sm;
-    } else {
-        wpc = 4;
-        grid = 0;
-    }
-    const size_t smem = burgers_smem_bytes(p->b.N, wpc);
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (grid == 0) {
-        int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * wpc, smem));
-        if (per_sm < 1) per_sm = 1;
-        grid = per_sm * n_sm;
-        const long long need = (n_chains + wpc - 1) / wpc;
-        if (grid > need) grid = (int)need;
-    }
-    sched_init_kernel<<<(unsigned)((2 * n_chains + 255) / 256 < 1184 ? (2 * n_chains + 255) / 256 : 1184), 256, 0, st>>>(C.sched, n_chains);
-    CUDA_TRY(cudaGetLastError());
-    kern<<<grid, 32 * wpc, smem, st>>>(p->b, S, C, n_chains, n_steps, chunk);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
-template <int NUM, int TM>
-static int burgers_launch_team_forward(ipmcmc_problem *p, long long n, const double *u, double *G, double *phi,
-                                       double *state, long long *work, cudaStream_t st) {
-    const size_t smem = burgers_team_smem_bytes(p->b.N);
-    auto kern = burgers_team_forward_kernel<32, NUM, TM>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid_for(n), 32 * TM, smem, st>>>(p->b, n, u, G, phi, state, work);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-template <int NUM, int TM>
-static int burgers_launch_team_chain(ipmcmc_problem *p, const SamplerDev &S, const ChainBufDev &C, long long n_chains,
-                                     long long n_steps, cudaStream_t st) {
-    const size_t smem = burgers_team_smem_bytes(p->b.N);
-    auto kern = burgers_team_chain_kernel<32, NUM, TM>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid_for(n_chains), 32 * TM, smem, st>>>(p->b, S, C, n_chains, n_steps);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
 #define BURGERS_TEAM_DISPATCH(FN, ...)                                                                  \
     do {                                                                                                \
         const bool fused = p->numerics == IPMCMC_NUMERICS_FUSED;                                        \
-        if (p->b.N == 2048) return fused ? FN<NUM_FUSED, 2>(__VA_ARGS__) : FN<NUM_EXACT, 2>(__VA_ARGS__); \
-        if (p->b.N == 4096) return fused ? FN<NUM_FUSED, 4>(__VA_ARGS__) : FN<NUM_EXACT, 4>(__VA_ARGS__); \
+        if (p->b.N == 2048) return cu(fused ? FN<NUM_FUSED, 2>(__VA_ARGS__) : FN<NUM_EXACT, 2>(__VA_ARGS__)); \
+        if (p->b.N == 4096) return cu(fused ? FN<NUM_FUSED, 4>(__VA_ARGS__) : FN<NUM_EXACT, 4>(__VA_ARGS__)); \
     } while (0)
 
 #define BURGERS_CASE(FN, C, ...)                                                                        \
     case C:                                                                                             \
-        if (fused) return padded ? FN<C, NUM_FUSED, true>(__VA_ARGS__) : FN<C, NUM_FUSED, false>(__VA_ARGS__); \
-        return padded ? FN<C, NUM_EXACT, true>(__VA_ARGS__) : FN<C, NUM_EXACT, false>(__VA_ARGS__);
+        if (fused) return cu(padded ? FN<C, NUM_FUSED, true>(__VA_ARGS__) : FN<C, NUM_FUSED, false>(__VA_ARGS__)); \
+        return cu(padded ? FN<C, NUM_EXACT, true>(__VA_ARGS__) : FN<C, NUM_EXACT, false>(__VA_ARGS__));
 
 #define BURGERS_DISPATCH(FN, ...)                                                       \
     do {                                                                                \
@@ -349,8 +269,8 @@ extern "C" int ipmcmc_forward(ipmcmc_problem *p, int64_t n, const double *u_dev,
     cudaStream_t st = (cudaStream_t)stream;
     if (p->model == IPMCMC_MODEL_BURGERS) {
         if (p->b.N > 1024)
-            BURGERS_TEAM_DISPATCH(burgers_launch_team_forward, p, n, u_dev, G_dev, phi_dev, state_dev, (long long *)work_dev, st);
-        BURGERS_DISPATCH(burgers_launch_forward, p, n, u_dev, G_dev, phi_dev, state_dev, (long long *)work_dev, st);
+            BURGERS_TEAM_DISPATCH(burgers_launch_team_forward, p->b, n, u_dev, G_dev, phi_dev, state_dev, (long long *)work_dev, st);
+        BURGERS_DISPATCH(burgers_launch_forward, p->b, n, u_dev, G_dev, phi_dev, state_dev, (long long *)work_dev, st);
     }
     if (!state_dev) return fail(IPMCMC_EINVAL, "Lorenz forward needs state_dev (carried initial condition)");
     const int groups = lorenz_groups(p->l.K);
@@ -445,17 +365,17 @@ extern "C" int ipmcmc_run(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, const
         int wpc = b->warps_per_cta > 0 ? b->warps_per_cta : 4;
         if (wpc > 8) return fail(IPMCMC_EINVAL, "warps_per_cta=%d > 8", wpc);
         if (b->slot_chain_dev && b->n_slots < 1) return fail(IPMCMC_EINVAL, "slot_chain_dev without n_slots");
-        if (p->b.N > 1024) BURGERS_TEAM_DISPATCH(burgers_launch_team_chain, p, S, C, n_chains, n_steps, st);
+        if (p->b.N > 1024) BURGERS_TEAM_DISPATCH(burgers_launch_team_chain, p->b, S, C, n_chains, n_steps, st);
         if (b->sched_dev) {
-            if (b->sched_len < sched_len(n_chains))
+            if (b->sched_len < burgers_sched_len(n_chains))
                 return fail(IPMCMC_EINVAL, "sched_len=%lld < 3*n_chains+2", (long long)b->sched_len);
             if (n_chains >= (1LL << 31)) return fail(IPMCMC_EUNSUPPORTED, "dynamic scheduler: n_chains >= 2^31");
             int chunk = b->sched_chunk > 0 ? b->sched_chunk : 1;
             if (const char *e = getenv("IPMCMC_SCHED_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;  // experiments
             C.sched = (long long *)b->sched_dev;
-            BURGERS_DISPATCH(burgers_launch_chain_queue, p, S, C, n_chains, n_steps, chunk, st);
+            BURGERS_DISPATCH(burgers_launch_chain_queue, p->b, S, C, n_chains, n_steps, chunk, st);
         }
-        BURGERS_DISPATCH(burgers_launch_chain, p, S, C, n_chains, n_steps, wpc, st);
+        BURGERS_DISPATCH(burgers_launch_chain, p->b, S, C, n_chains, n_steps, wpc, st);
     }
     const int groups = lorenz_groups(p->l.K);
     const long long warps = (n_chains + groups - 1) / groups;
@@ -659,16 +579,3 @@ extern "C" int ipmcmc_fp64_peak(int32_t iters, double *tflops_out) {
     *tflops_out = best;
     return 0;
 }
-
-#if IPMCMC_PROF
-// developer instrumentation only (tools/overhead_probe.py); not declared in include/ipmcmc.h
-extern "C" int ipmcmc_prof_read(unsigned long long *out16, int reset) {
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out16, ipmcmc::g_prof, sizeof(unsigned long long) * 16);
-    if (reset) {
-        unsigned long long z[16] = {0};
-        cudaMemcpyToSymbol(ipmcmc::g_prof, z, sizeof(z));
-    }
-    return 0;
-}
-#endif

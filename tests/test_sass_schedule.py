@@ -46,16 +46,21 @@ def test_bench_kernel_time_step_loop_schedule(tmp_path):
     from ip_mcmc_b200 import build
     lib = build.build()
     sass = tmp_path / "lib.sass"
-    # the 1024 x 256 bench shape: CPL = 8, FUSED numerics, dynamic scheduler, one CTA per SM
-    fun = "_ZN6ipmcmc26burgers_chain_queue_kernelILi8ELi1ELb0ELi1EEEvNS_10BurgersDevENS_10SamplerDevENS_11ChainBufDevExxi"
+    # the 1024 x 256 bench shape: CPL = 8, FUSED numerics, dynamic scheduler, 128-register build
+    fun = "_ZN6ipmcmc26burgers_chain_queue_kernelILi8ELi1ELb0ELi2EEEvNS_10BurgersDevENS_10SamplerDevENS_11ChainBufDevExxi"
     with open(sass, "w") as f:
         subprocess.run(["cuobjdump", "-sass", "-fun", fun, lib], stdout=f, stderr=subprocess.DEVNULL, check=False)
-    loops = _time_step_loops(str(sass), "burgers_chain_queue_kernelILi8ELi1ELb0ELi1E")
-    # two rotated time-step loops (burgers.cuh, time_loop_pipelined): the select-free one for positive
-    # states and the general one; both include the rarely taken ~50-instruction repair block
-    assert len(loops) == 2, "expected the positive-state and the general time-step loop, found %r" % (loops,)
-    pos, gen = sorted(loops, key=lambda t: t[1])
-    assert pos[1] <= 120 and gen[1] <= 140, "fp64 instructions per 256-cell time step grew: %r" % (loops,)
-    assert pos[2] <= 480 and gen[2] <= 540, (
-        "ptxas serialised a time-step loop (static stall sums %d / %d, limits 480 / 540): unrelated edits move "
+    loops = _time_step_loops(str(sass), "burgers_chain_queue_kernelILi8ELi1ELb0ELi2E")
+    # two rotated time-step loops (burgers.cuh, time_loop_pipelined), each nested in the loop that repairs a
+    # wrong high-word guess: keep the innermost ones -- the select-free one (positive states) and the general one
+    inner = {}
+    for n_ins, n_f64, stalls in loops:
+        key = "pos" if n_f64 < 125 else "gen"
+        if key not in inner or n_ins < inner[key][0]:
+            inner[key] = (n_ins, n_f64, stalls)
+    assert set(inner) == {"pos", "gen"}, "expected the positive-state and the general time-step loop, found %r" % (loops,)
+    pos, gen = inner["pos"], inner["gen"]
+    assert pos[1] <= 116 and gen[1] <= 134, "fp64 instructions per 256-cell time step grew: %r" % (loops,)
+    assert pos[2] <= 330 and gen[2] <= 400, (
+        "ptxas serialised a time-step loop (static stall sums %d / %d, limits 330 / 400): unrelated edits move "
         "its register allocation; see tools/sass_loops.py and DESIGN.md section 4.1" % (pos[2], gen[2]))

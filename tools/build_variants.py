@@ -19,13 +19,15 @@ def one(spec):
     tag, _, flags = spec.partition(":")
     flags = [f for f in flags.split(",") if f]
     lib = os.path.join(OUT, "libipmcmc_%s.so" % tag)
-    cmd = [os.environ.get("NVCC", "nvcc")] + B.NVCC_FLAGS + flags + ["-o", lib] + B.SOURCES
-    r = subprocess.run(cmd, cwd=B.CSRC, capture_output=True, text=True)
-    return tag, r.returncode, r.stderr[-2000:]
+    try:
+        B.compile_units(lib, extra_flags=flags, obj_dir=os.path.join(OUT, "obj_" + tag))
+    except RuntimeError as e:
+        return tag, 1, str(e)[-2000:]
+    return tag, 0, ""
 
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    with ThreadPoolExecutor(4) as ex:
+    with ThreadPoolExecutor(2) as ex:
         for tag, rc, err in ex.map(one, sys.argv[1:]):
             print(tag, "ok" if rc == 0 else "FAILED\n" + err)
