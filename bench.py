@@ -35,7 +35,7 @@ PRIOR_MEAN = np.array([1.5, 0.25, -0.5])
 WORKLOADS = {
     "burgers_pcn_256": dict(model="burgers", N=256, chains=1024, mcmc_steps=200, beta=0.25),
     "burgers_pcn_1024": dict(model="burgers", N=1024, chains=8192, mcmc_steps=4, beta=0.25),
-    "lorenz_rw": dict(model="lorenz", chains=4096, mcmc_steps=2, delta=0.125, T=20.0),
+    "lorenz_rw": dict(model="lorenz", chains=4096, mcmc_steps=8, delta=0.125, T=20.0),
 }
 
 

@@ -210,7 +210,8 @@ typedef struct ipmcmc_chain_buffers {
     const int32_t *slot_chain_dev; /* [n_slots]                                                  */
     int32_t n_slots;
     int32_t warps_per_cta;
-    /* optional scratch of the DYNAMIC STEP SCHEDULER (Burgers, N <= 1024; results do not depend on
+    /* optional scratch of the DYNAMIC STEP SCHEDULER (Burgers with N <= 1024, where the work unit is a
+       chain, and Lorenz, where it is a warp's group of floor(32/K) chains; results do not depend on
        it): int64 [sched_len >= 3*n_chains + 2], contents irrelevant on entry.  When given, persistent
        warps take (chain, sched_chunk steps) work items from a FIFO of ready chains instead of a
        fixed chain -> warp map, which keeps every SM sub-partition busy until the launch ends although

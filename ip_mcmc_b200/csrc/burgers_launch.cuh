@@ -24,7 +24,4 @@ template <int NUM, int TM>
 cudaError_t burgers_launch_team_chain(const BurgersDev &b, const SamplerDev &S, const ChainBufDev &C,
                                       long long n_chains, long long n_steps, cudaStream_t st);
 
-// scratch length of the dynamic step scheduler (int64 words) for n_chains chains
-inline long long burgers_sched_len(long long n_chains) { return 3 * n_chains + 2; }
-
 }  // namespace ipmcmc

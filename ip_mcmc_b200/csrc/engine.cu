@@ -367,7 +367,7 @@ extern "C" int ipmcmc_run(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, const
         if (b->slot_chain_dev && b->n_slots < 1) return fail(IPMCMC_EINVAL, "slot_chain_dev without n_slots");
         if (p->b.N > 1024) BURGERS_TEAM_DISPATCH(burgers_launch_team_chain, p->b, S, C, n_chains, n_steps, st);
         if (b->sched_dev) {
-            if (b->sched_len < burgers_sched_len(n_chains))
+            if (b->sched_len < sched_len(n_chains))
                 return fail(IPMCMC_EINVAL, "sched_len=%lld < 3*n_chains+2", (long long)b->sched_len);
             if (n_chains >= (1LL << 31)) return fail(IPMCMC_EUNSUPPORTED, "dynamic scheduler: n_chains >= 2^31");
             int chunk = b->sched_chunk > 0 ? b->sched_chunk : 1;
@@ -380,6 +380,25 @@ extern "C" int ipmcmc_run(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, const
     const int groups = lorenz_groups(p->l.K);
     const long long warps = (n_chains + groups - 1) / groups;
     const int wpc = lorenz_warps_per_cta(warps, p->l.K);
+    if (b->sched_dev) {
+        // dynamic step scheduler over the warps' chain groups: persistent warps, one wave (255 registers:
+        // 8 warps per SM at most; the queue needs every launched CTA resident)
+        if (b->sched_len < sched_len(warps)) return fail(IPMCMC_EINVAL, "sched_len=%lld too short", (long long)b->sched_len);
+        int dev = 0, n_sm = 148;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        const long long resident = (long long)n_sm * (8 / wpc);
+        long long ctas = (warps + wpc - 1) / wpc;
+        if (ctas > resident) ctas = resident;
+        int chunk = b->sched_chunk > 0 ? b->sched_chunk : 1;
+        if (const char *e = getenv("IPMCMC_SCHED_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;  // experiments
+        C.sched = (long long *)b->sched_dev;
+        sched_init_kernel<<<(unsigned)((2 * warps + 255) / 256 < 1184 ? (2 * warps + 255) / 256 : 1184), 256, 0, st>>>(C.sched, warps);
+        CUDA_TRY(cudaGetLastError());
+        LORENZ_DISPATCH(lorenz_chain_queue_kernel, p->l.J, p->l.K, p->numerics,
+                        <<<(int)ctas, 32 * wpc, wpc * lorenz_smem_bytes(p->l.K), st>>>(p->l, S, C, n_chains, n_steps, chunk));
+        return 0;
+    }
     LORENZ_DISPATCH(lorenz_chain_kernel, p->l.J, p->l.K, p->numerics,
                     <<<grid_for((warps + wpc - 1) / wpc), 32 * wpc, wpc * lorenz_smem_bytes(p->l.K), st>>>(
                         p->l, S, C, n_chains, n_steps));

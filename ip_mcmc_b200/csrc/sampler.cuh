@@ -108,6 +108,17 @@ __device__ __forceinline__ bool constraint_ok(const SamplerDev &S, const Group &
     return (bal & gmask) == gmask;
 }
 
+// Number of recorded steps in [record_start, g): recorded are the g with (g - record_start + 1) % interval == 0
+// (sampler.py:23-28).
+__device__ __forceinline__ long long recorded_before(const SamplerDev &S, long long g) {
+    if (!(S.record_interval > 0 && g > S.record_start)) return 0;
+    return (g - S.record_start) / S.record_interval;
+}
+__device__ __forceinline__ bool records_step(const SamplerDev &S, long long gstep) {
+    if (!(S.record_interval > 0 && gstep >= S.record_start)) return false;
+    return ((gstep - S.record_start + 1) % S.record_interval) == 0;
+}
+
 struct Welford {
     double count, mean, m2;
     __device__ __forceinline__ void add(double x) {

@@ -217,8 +217,13 @@ class ChainBatch:
         self.launches = 0
         self.placement = None
         self._work_prev = None
-        self.sched = None          # scratch of the dynamic step scheduler (Burgers, N <= 1024)
+        self.sched = None          # scratch of the dynamic step scheduler (Burgers N <= 1024, Lorenz)
         self.sched_chunk = 0       # Metropolis steps per work item; 0 = min(4, max(1, n_steps // 64)) per launch
+        if problem.kind == _lib.MODEL_LORENZ:
+            if scheduler == "dynamic":
+                self.sched = torch.empty((3 * self.n + 2,), dtype=torch.int64, device=dev)
+            elif scheduler != "static":
+                raise ValueError("scheduler must be 'dynamic' or 'static'")
         if problem.kind == _lib.MODEL_BURGERS:
             n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
             if scheduler == "dynamic" and problem.model.N <= 1024:

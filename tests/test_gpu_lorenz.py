@@ -190,3 +190,25 @@ def test_lorenz_chain_first_steps_and_statistics(G):
     acc = s.accepter.ratio()
     assert 0.25 < acc < 0.9, acc          # reference: 24/40 at T=2, "around 0.6" at T=20 (lorenz.org:277-279)
     assert s.last_run["counters"]["work_a"] > 33 * 30 * 2 * 50
+
+
+@pytest.mark.parametrize("n_chains,n_samples,steps_per_launch", [(33, 6, None), (1003, 5, 2), (7, 4, 3)])
+def test_lorenz_dynamic_scheduler_bit_identical_to_static(G, n_chains, n_samples, steps_per_launch):
+    """The dynamic step scheduler of the Lorenz kernel (work unit = a warp's group of 5 chains, the carried
+    initial condition travelling through L2 between work items) is pure scheduling: samples, carried
+    states, counters and moments equal the static kernel bit for bit (ragged last group, several launches,
+    more groups than SMs)."""
+    import ip_mcmc_b200 as M
+    f, pot, prior, p = _lorenz_setup(0.5, numerics="fused")
+    mk = lambda: M.MCMCSampler(M.ConstStepStandardRWProposer(0.125, prior),
+                               M.CountedAccepter(M.StandardRWAccepter(pot, prior)), np.random.default_rng(5))
+    a, b = mk(), mk()
+    out_a = a.run(p["u0"], n_samples, 2, 1, n_chains=n_chains, steps_per_launch=steps_per_launch, scheduler="static")
+    out_b = b.run(p["u0"], n_samples, 2, 1, n_chains=n_chains, steps_per_launch=steps_per_launch, scheduler="dynamic")
+    ca, cb = a.last_run["chains"], b.last_run["chains"]
+    assert ca.sched is None and cb.sched is not None
+    assert np.array_equal(out_a, out_b)
+    assert torch.equal(ca.model_state, cb.model_state)
+    assert torch.equal(ca.counters, cb.counters) and torch.equal(ca.u, cb.u) and torch.equal(ca.phi, cb.phi)
+    assert torch.equal(ca.mom_count, cb.mom_count) and torch.equal(ca.mom_mean, cb.mom_mean) and torch.equal(ca.mom_m2, cb.mom_m2)
+    assert a.accepter.calls == b.accepter.calls and a.accepter.accepts == b.accepter.accepts

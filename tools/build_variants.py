@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Build kernel variants of libipmcmc.so for A/B measurements on the GPU box:
-    python tools/build_variants.py tag1:-DIPMCMC_UPWIND=1 tag2:-DIPMCMC_UPWIND=2,-DIPMCMC_CFL_CACHE=2
+    python tools/build_variants.py base: nopos:-DIPMCMC_POSPATH=0 plain:-DIPMCMC_PIPELINED=0
 writes gpurun_variants/libipmcmc_<tag>.so (git-ignored; travels with the snapshot).  Select one with
 IPMCMC_LIB=gpurun_variants/libipmcmc_<tag>.so."""
 import os
