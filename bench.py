@@ -80,7 +80,8 @@ def cpu_sample(wl, n_steps, n_workers, u_start):
 
 
 def cpu_steps_for(wl):
-    return {"burgers": 150 if wl.get("N", 0) <= 256 else 6, "lorenz": 2}[wl["model"]]
+    # bounded sample: ~10 s of work per process at N = 256 (~70 chain-steps/s/core), ~15 s at N = 1024, ~12 s Lorenz
+    return {"burgers": 600 if wl.get("N", 0) <= 256 else 12, "lorenz": 2}[wl["model"]]
 
 
 def posterior_start(wl):

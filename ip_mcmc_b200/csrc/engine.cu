@@ -1,5 +1,7 @@
-// libipmcmc.so -- C ABI (include/ipmcmc.h) over the sm_100a kernels.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+// libipmcmc.so -- C ABI (include/ipmcmc.h) over the sm_100a kernels.  This unit holds the ABI, the Lorenz
+// kernels and the small kernels; the Burgers kernels are compiled from burgers_inst.cu, one unit per
+// cells-per-lane value.  Build (ip_mcmc_b200/build.py): nvcc -gencode arch=compute_100a,code=sm_100a -O3
+// -lineinfo -fmad=false -c <unit> ..., then nvcc -shared.
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
