@@ -56,12 +56,14 @@ class MCMCSampler:
         return spec, pot, a
 
     def run(self, u_0, n_samples, burn_in=1000, sample_interval=200, n_chains=None, chain_offset=0,
-            steps_per_launch=None, return_device=False, recompute_phi_u=None, scheduler=None):
+            steps_per_launch=None, return_device=False, recompute_phi_u=None, scheduler=None, out=None):
         """Same step accounting as the reference (sampler.py:18-28): max(0, burn_in - interval)
         unrecorded steps, then n_samples * interval steps recording every interval-th state.
 
         Returns ndarray [n_samples, d] for a single chain (u_0 of shape (d,), n_chains None) or
         [n_chains, n_samples, d] for a batch.  Statistics of the run are left in `self.last_run`.
+        `out`: optional preallocated host buffer for the samples (NumPy array or torch CPU tensor of
+        n_chains * n_samples * d float64; a PINNED torch tensor makes the device->host copy a single DMA).
         """
         if sample_interval < 1:
             raise ValueError("sample_interval must be >= 1")
@@ -110,9 +112,17 @@ class MCMCSampler:
             c.accepts += int(self.last_run["counters"]["accepts"])
         if return_device:
             return trace[0] if single else trace
-        out = trace.cpu().numpy()
-        self.last_run["d2h_bytes"] = out.nbytes + pooled_h.nbytes
-        return out[0] if single else out
+        if out is not None:
+            dst = out if torch.is_tensor(out) else torch.from_numpy(out)
+            if dst.dtype != F64 or dst.numel() != trace.numel() or not dst.is_contiguous():
+                raise ValueError("out must be a contiguous float64 buffer of %d elements" % trace.numel())
+            dst.view(trace.shape).copy_(trace, non_blocking=True)
+            torch.cuda.current_stream(problem.device).synchronize()
+            res = dst.view(trace.shape).numpy()
+        else:
+            res = trace.cpu().numpy()
+        self.last_run["d2h_bytes"] = res.nbytes + pooled_h.nbytes
+        return res[0] if single else res
 
     @classmethod
     def autocorr(cls, x):

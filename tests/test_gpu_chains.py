@@ -273,3 +273,21 @@ def test_grid_refinement_study_driver(G):
         h = out[N]["histogram"]
         assert h.shape == (20, 20, 20) and abs(h.sum() * 0.05 ** 3 - 1) < 1e-9
         assert 0.01 < out[N]["acceptance"] < 0.99
+
+
+def test_run_into_preallocated_host_buffer(G):
+    """`out=`: samples land in a caller-owned (pinned torch or NumPy) host buffer, identical to the
+    returned-array path; wrong sizes are refused."""
+    import ip_mcmc_b200 as M
+    f, pot, prior, _ = G.burgers_setup(64, "fused")
+    mk = lambda: M.MCMCSampler(M.ConstSteppCNProposer(0.25, prior), M.CountedAccepter(M.pCNAccepter(pot)),
+                               np.random.default_rng(3))
+    ref = mk().run(np.zeros(3), 9, 0, 1, n_chains=17)
+    pinned = torch.empty((17, 9, 3), dtype=torch.float64).pin_memory()
+    got = mk().run(np.zeros(3), 9, 0, 1, n_chains=17, out=pinned)
+    assert np.array_equal(got, ref) and np.array_equal(pinned.numpy(), ref)
+    arr = np.empty((17, 9, 3))
+    got2 = mk().run(np.zeros(3), 9, 0, 1, n_chains=17, out=arr)
+    assert np.array_equal(arr, ref) and got2 is not None
+    with pytest.raises(ValueError):
+        mk().run(np.zeros(3), 9, 0, 1, n_chains=17, out=np.empty((17, 8, 3)))
