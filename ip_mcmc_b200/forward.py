@@ -41,7 +41,7 @@ class BurgersFVM(ForwardModel):
     utilities.py:93-98) so that they are bit-identical.
 
     numerics: "exact" (reference rounding order, bit-identical results) or "fused"
-    (FMA-contracted update, ~1e-13 relative agreement, fewer fp64 instructions).
+    (FMA-contracted update, 1e-13 ... 3e-11 relative agreement in G depending on the grid, fewer fp64 instructions).
     """
     kind = _lib.MODEL_BURGERS
 
