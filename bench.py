@@ -97,7 +97,8 @@ def run_reference(args, wl, name, out_fd):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = cpu_steps_for(wl)
+    # bounded sample per bench step, shrunk for long runs so that the whole arm stays within a few minutes
+    n = max(1, min(cpu_steps_for(wl), cpu_steps_for(wl) * 12 // max(args.steps, 1)))
     u_start = posterior_start(wl)
     for _ in range(args.warmup if args.warmup < 2 else 1):      # process start-up / import warm-up
         cpu_sample(wl, 1, cores, u_start)
