@@ -56,7 +56,8 @@ cudaError_t burgers_launch_chain_queue(const BurgersDev &b, const SamplerDev &S,
     // Register budget (measured on B200; tools/ab_bench.sh): up to 8 cells per lane the 128-register
     // build schedules the time step best at every batch size (1024 x 256: 67 % of the fp64 peak against
     // 61 % with 255 registers); from 16 cells per lane on it spills the state, and 255 registers with
-    // half the resident warps win by far (8192 x 1024: 81 % against 66 %).
+    // half the resident warps win by far (8192 x 1024: 81 % against 66 %; 88 % with the rotated loop, which
+    // only fits the 255-register build at 32 cells per lane).
     int wpc, grid;
     const bool small = n_chains <= 8LL * n_sm;
     constexpr int MINB = CPL >= 16 ? 1 : 2;
