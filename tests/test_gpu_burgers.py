@@ -47,8 +47,8 @@ def test_forward_fused_within_tolerance(G, N):
 def test_forward_fused_positive_and_sign_changing_states(G, N):
     """FUSED runs a select-free time loop when the initial data are positive everywhere and the general
     (upwind-select) loop otherwise (burgers.cuh, flux_fused<.., POS>); both must agree with the
-    reference-order solver to the north-star tolerance, on padded and unpadded layouts, for the rotated
-    loop (<= 8 cells per lane) and the plain one."""
+    reference-order solver to the north-star tolerance, on padded and unpadded layouts and for every
+    cells-per-lane instantiation of the rotated time loop."""
     P = B.BurgersProblem(N)
     pm = P.prior_mean
     params = np.array([
