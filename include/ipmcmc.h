@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define IPMCMC_ABI_VERSION 1
+#define IPMCMC_ABI_VERSION 2
 
 #define IPMCMC_MAX_DIM 32   /* parameter dimension d   (3 in every reference script)          */
 #define IPMCMC_MAX_OBS 64   /* observation dimension q (5 Burgers, 5K = 30 Lorenz)            */
@@ -111,7 +111,8 @@ typedef struct ipmcmc_burgers_desc {
  * from solve to solve per chain (lorenz_mcmc.py:66) in a caller-owned [n_chains, K*(J+1)] buffer.
  * ------------------------------------------------------------------------------------------ */
 typedef struct ipmcmc_lorenz_desc {
-    int32_t K, J;             /* slow variables / fast variables per slow variable              */
+    int32_t K, J;             /* slow variables (3 <= K <= IPMCMC_MAX_OBS/5 = 12) / fast variables per
+                                 slow variable (J in {1,2,4,8})                                  */
     int32_t max_attempts;     /* cap on RK attempts per solve (<=0: 1<<20)                      */
     int32_t numerics;         /* IPMCMC_NUMERICS_EXACT: right-hand side in the reference's rounding
                                  order (lorenz.py:73-101); IPMCMC_NUMERICS_FUSED: contracted RHS  */
@@ -175,7 +176,8 @@ typedef struct ipmcmc_sampler_desc {
     const double *box_hi;     /* host [d]                                                       */
     const double *box_shift;  /* host [d]                                                       */
     uint64_t seed;            /* Philox4x32-10 key = (seed lo, global chain id)                 */
-    int64_t chain_offset;     /* global id of local chain 0 (multi-GPU sharding)                */
+    int64_t chain_offset;     /* global id of local chain 0 (multi-GPU sharding); global ids must
+                                 stay below 2^32 (the Philox key holds 32 bits of it)           */
     int64_t first_step;       /* global index of the first step of this launch                  */
     int64_t record_start;     /* first step of the sampling phase = max(0, burn_in - interval)  */
     int64_t record_interval;  /* sample_interval (sampler.py:25-28); <=0: record nothing        */
@@ -227,25 +229,43 @@ int ipmcmc_run(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, const ipmcmc_cha
 
 /* Pool per-chain Welford moments and counters of n_chains chains into
  *   pooled_dev[0] = n, [1..d] = mean, [1+d..2d] = M2, then the 6 counters as doubles
- * (2d + 7 doubles) with Chan's parallel merge -- the buffer each rank all-reduces. */
+ * (2d + 7 doubles) with Chan's parallel merge as a fixed tree (deterministic; two small launches whose
+ * cost does not grow with n_chains beyond reading 8(1+2d)+48 bytes per chain) -- the buffer each rank
+ * contributes to the ONE collective of a multi-GPU run (ip_mcmc_b200/parallel.py).
+ *   replaces the post-hoc np.mean / np.var over sample arrays and CountedAccepter.ratio()
+ *   (burgers_mcmc.py:136-143, accepter.py:29-36) for batches whose samples are not materialised.
+ * scratch_dev: caller-owned device scratch of ipmcmc_pool_scratch_bytes(n_chains, dim) bytes, or NULL
+ * (then a stream-ordered allocation is made and freed inside the call). */
+int64_t ipmcmc_pool_scratch_bytes(int64_t n_chains, int32_t dim);
 int ipmcmc_pool_moments(int64_t n_chains, int32_t dim, const double *mom_count_dev,
                         const double *mom_mean_dev, const double *mom_m2_dev,
-                        const int64_t *counters_dev, double *pooled_dev, void *stream);
+                        const int64_t *counters_dev, double *pooled_dev, void *scratch_dev,
+                        int64_t scratch_bytes, void *stream);
 
 /* --------------------------------------------------------------------------------------------
- * Host-buffer convenience path (what a non-Python binding would call; used for the e2e number):
- * copies u0 (and the Lorenz IC) host->device, runs n_steps, copies the recorded samples,
- * per-chain counters and pooled moments device->host, synchronises.
- *   u0_host        [n_chains, d]
- *   model_state_host  Lorenz [n_chains, K*(J+1)] IN/OUT, Burgers NULL
- *   samples_host   [n_chains, n_record, d] or NULL
- *   counters_host  [n_chains, 6] or NULL
- *   pooled_host    [2d + 7] or NULL
+ * Host-buffer entry point -- what a non-Python binding of MCMCSampler.run (sampler.py:12-33) calls, and
+ * what bench.py times as `e2e_c_abi`: copies u0 (and the Lorenz IC) host->device, runs n_steps with the
+ * SAME kernels and scheduler as the device-buffer path (dynamic step scheduler where it applies), copies
+ * the recorded samples, final states, per-chain counters and pooled moments device->host, synchronises.
+ * All device memory is one stream-ordered arena allocated and freed inside the call.
  * ------------------------------------------------------------------------------------------ */
+typedef struct ipmcmc_host_io {
+    const double *u0_host;     /* IN  [n_chains, d] initial states                                  */
+    const double *phi0_host;   /* IN  [n_chains] Phi(u0) from a previous call (phi_host), or NULL:
+                                      the kernel evaluates it (one extra solve per chain)           */
+    double *model_state_host;  /* IN/OUT Lorenz [n_chains, K*(J+1)] carried IC; Burgers NULL        */
+    double *samples_host;      /* OUT [n_chains, n_record, d] recorded samples, or NULL             */
+    int64_t n_record;          /*     capacity per chain of samples_host                            */
+    double *u_host;            /* OUT [n_chains, d] final states, or NULL                           */
+    double *phi_host;          /* OUT [n_chains] Phi(final state), or NULL                          */
+    int64_t *counters_host;    /* OUT [n_chains, 6], or NULL                                        */
+    double *pooled_host;       /* OUT [2d + 7] pooled moments + counters, or NULL                   */
+    int32_t scheduler;         /* 0: dynamic step scheduler where available (default), 1: static    */
+    int32_t sched_chunk;       /* Metropolis steps per work item (<= 0: min(4, max(1, n_steps/64))) */
+} ipmcmc_host_io;
+
 int ipmcmc_sample_host(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, int64_t n_chains,
-                       int64_t n_steps, const double *u0_host, double *model_state_host,
-                       double *samples_host, int64_t n_record, int64_t *counters_host,
-                       double *pooled_host, void *stream);
+                       int64_t n_steps, const ipmcmc_host_io *io, void *stream);
 
 /* --------------------------------------------------------------------------------------------
  * Probes used by the parity tests and the roofline measurement

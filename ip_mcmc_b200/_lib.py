@@ -5,6 +5,7 @@ import os
 
 from . import build as _build
 
+ABI_VERSION = 2
 MAX_DIM = 32
 MAX_OBS = 64
 N_COUNTERS = 6
@@ -58,6 +59,13 @@ class ChainBuffers(C.Structure):
                 ("sched_chunk", C.c_int32), ("reserved", C.c_int32)]
 
 
+class HostIO(C.Structure):
+    _fields_ = [("u0_host", c_double_p), ("phi0_host", c_double_p), ("model_state_host", c_double_p),
+                ("samples_host", c_double_p), ("n_record", C.c_int64), ("u_host", c_double_p),
+                ("phi_host", c_double_p), ("counters_host", c_int64_p), ("pooled_host", c_double_p),
+                ("scheduler", C.c_int32), ("sched_chunk", C.c_int32)]
+
+
 # every symbol include/ipmcmc.h declares
 SYMBOLS = {
     "ipmcmc_burgers_create": (C.c_int, [C.POINTER(BurgersDesc), C.POINTER(C.c_void_p)]),
@@ -67,10 +75,11 @@ SYMBOLS = {
                                  C.c_void_p, C.c_void_p]),
     "ipmcmc_run": (C.c_int, [C.c_void_p, C.POINTER(SamplerDesc), C.POINTER(ChainBuffers), C.c_int64,
                              C.c_int64, C.c_void_p]),
+    "ipmcmc_pool_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
     "ipmcmc_pool_moments": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                      C.c_void_p, C.c_void_p]),
-    "ipmcmc_sample_host": (C.c_int, [C.c_void_p, C.POINTER(SamplerDesc), C.c_int64, C.c_int64, c_double_p,
-                                     c_double_p, c_double_p, C.c_int64, c_int64_p, c_double_p, C.c_void_p]),
+                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ipmcmc_sample_host": (C.c_int, [C.c_void_p, C.POINTER(SamplerDesc), C.c_int64, C.c_int64, C.POINTER(HostIO),
+                                     C.c_void_p]),
     "ipmcmc_lorenz_rhs": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
     "ipmcmc_lorenz_rk45_attempt": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
@@ -110,7 +119,7 @@ def load():
         fn = getattr(lib, name)      # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.ipmcmc_abi_version() != 1:
+    if lib.ipmcmc_abi_version() != ABI_VERSION:
         raise EngineError("ABI version mismatch")
     _lib = lib
     return lib

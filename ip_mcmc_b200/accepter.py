@@ -111,14 +111,17 @@ class pCNAccepter(ProbabilisticAccepter):
 
 def device_spec(accepter):
     """Unwrap CountedAccepter / ConstrainAccepter decorators around a StandardRW/pCN accepter.
-    Returns dict(kind, potential, prior, constraint, counted)."""
-    counted = None
+    Returns dict(kind, potential, prior, constraint, counted), `counted` a list of
+    (CountedAccepter, inside_constraint) pairs.  A counter that sits INSIDE the ConstrainAccepter -- the
+    reference's Wasserstein scripts use ConstrainAccepter(CountedAccepter(StandardRWAccepter), is_valid),
+    burgers_wasserstein_grid.py:150-160 -- never sees a constraint-rejected proposal (accepter.py:52-55),
+    so its `calls` exclude them; one that wraps the ConstrainAccepter counts every step."""
+    counted = []
     constraint = None
     a = accepter
     while True:
         if isinstance(a, CountedAccepter):
-            if counted is None:
-                counted = a
+            counted.append((a, constraint is not None))
             a = a.accepter
         elif isinstance(a, ConstrainAccepter):
             if constraint is not None:
@@ -136,3 +139,10 @@ def device_spec(accepter):
                         "pCNAccepter, optionally wrapped in CountedAccepter/ConstrainAccepter)" % (a,))
     return dict(kind=a.kind, potential=a.theta, prior=getattr(a, "prior", None), constraint=constraint,
                 counted=counted, outer_counted=isinstance(accepter, CountedAccepter))
+
+
+def credit_counters(spec, calls, accepts, constraint_rejects):
+    """Add the device counters of a run to every CountedAccepter of the stack (device_spec)."""
+    for c, inside in spec["counted"]:
+        c.calls += int(calls) - (int(constraint_rejects) if inside else 0)
+        c.accepts += int(accepts)

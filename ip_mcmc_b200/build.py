@@ -27,15 +27,35 @@ CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fm
 NVCC_FLAGS = CFLAGS      # (name kept for tools/)
 
 
+# headers each kind of unit includes (a unit is recompiled when its object is older than any of them)
+_COMMON = ["common.cuh", "philox.cuh", "sampler.cuh", "sched.cuh", "burgers.cuh", "burgers_launch.cuh",
+           os.path.join("..", "..", "include", "ipmcmc.h")]
+DEPS = {"engine.cu": _COMMON + ["lorenz.cuh", "lorenz_kernels.cuh"],
+        "burgers_inst.cu": _COMMON + ["burgers_kernels.cuh", "burgers_team.cuh", "burgers_launch_impl.cuh"]}
+
+
+def _mtime(f):
+    return os.path.getmtime(os.path.join(CSRC, f))
+
+
+def _unit_stale(unit, obj_dir):
+    name, src, _ = unit
+    obj = os.path.join(obj_dir, name + ".o")
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    return any(_mtime(f) > t for f in [src] + DEPS[src])
+
+
 def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    return any(_mtime(f) > t for f in SOURCES + HEADERS)
 
 
-def compile_units(out_lib, extra_flags=(), obj_dir=None, verbose=False):
-    """nvcc -c every translation unit (in parallel), then link them into out_lib."""
+def compile_units(out_lib, extra_flags=(), obj_dir=None, verbose=False, force=True):
+    """nvcc -c every (stale) translation unit in parallel, then link them into out_lib."""
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
     obj_dir = obj_dir or OBJ
@@ -44,6 +64,8 @@ def compile_units(out_lib, extra_flags=(), obj_dir=None, verbose=False):
     def one(unit):
         name, src, defs = unit
         obj = os.path.join(obj_dir, name + ".o")
+        if not force and not _unit_stale(unit, obj_dir):
+            return obj
         cmd = [nvcc] + CFLAGS + list(extra_flags) + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
         r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
         if r.returncode != 0:
@@ -65,7 +87,7 @@ def build(force=False, verbose=False):
     """Compile the library if it is missing or older than its sources. Returns the path."""
     if not force and not _stale():
         return LIB
-    return compile_units(LIB, verbose=verbose)
+    return compile_units(LIB, verbose=verbose, force=force)
 
 
 if __name__ == "__main__":

@@ -47,8 +47,31 @@ struct ipmcmc_problem {
     BurgersDev b;
     LorenzDev l;
     std::vector<void *> owned;   // device allocations freed in destroy
-    double *scratch = nullptr;   // device [2*MAX_DIM*MAX_DIM]: proposal factor | prior Cholesky
+    // Small sampler tables (proposal factor, prior Cholesky factor) by content: a table is uploaded once,
+    // synchronously, and never overwritten, so launches on different streams or with different samplers
+    // cannot race on it and repeated launches do not re-upload it.
+    struct Table {
+        std::vector<double> host;
+        double *dev;
+    };
+    std::vector<Table> tables;
 };
+
+static int cached_table(ipmcmc_problem *p, const double *host, size_t n, const double **dev) {
+    for (const auto &t : p->tables)
+        if (t.host.size() == n && memcmp(t.host.data(), host, n * sizeof(double)) == 0) {
+            *dev = t.dev;
+            return 0;
+        }
+    if (p->tables.size() >= 64) return fail(IPMCMC_EUNSUPPORTED, "more than 64 distinct sampler tables on one problem handle");
+    double *d = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d, n * sizeof(double)));
+    p->owned.push_back(d);
+    CUDA_TRY(cudaMemcpy(d, host, n * sizeof(double), cudaMemcpyHostToDevice));
+    p->tables.push_back(ipmcmc_problem::Table{std::vector<double>(host, host + n), d});
+    *dev = d;
+    return 0;
+}
 
 static int upload(ipmcmc_problem *p, const void *host, size_t bytes, void **dev) {
     CUDA_TRY(cudaMalloc(dev, bytes ? bytes : 8));
@@ -83,11 +106,6 @@ static int fill_potential(ipmcmc_problem *p, const ipmcmc_potential_desc &d, Pot
 }
 
 static int finish_create(ipmcmc_problem *p, ipmcmc_problem **out) {
-    void *dev;
-    int rc = upload(p, nullptr, 0, &dev);
-    if (rc) return rc;
-    CUDA_TRY(cudaMalloc((void **)&p->scratch, sizeof(double) * 2 * IPMCMC_MAX_DIM * IPMCMC_MAX_DIM));
-    p->owned.push_back(p->scratch);
     *out = p;
     return 0;
 }
@@ -158,7 +176,8 @@ extern "C" int ipmcmc_burgers_create(const ipmcmc_burgers_desc *d, ipmcmc_proble
 
 extern "C" int ipmcmc_lorenz_create(const ipmcmc_lorenz_desc *d, ipmcmc_problem **out) {
     if (!d || !out) return fail(IPMCMC_EINVAL, "NULL argument");
-    if (d->K < 3 || d->K > 32) return fail(IPMCMC_EUNSUPPORTED, "K=%d outside [3,32] (one lane per slow variable)", d->K);
+    if (d->K < 3 || 5 * d->K > IPMCMC_MAX_OBS)
+        return fail(IPMCMC_EUNSUPPORTED, "K=%d outside [3,%d] (one lane per slow variable; 5K observations <= IPMCMC_MAX_OBS)", d->K, IPMCMC_MAX_OBS / 5);
     if (d->J != 1 && d->J != 2 && d->J != 4 && d->J != 8) return fail(IPMCMC_EUNSUPPORTED, "J=%d not in {1,2,4,8}", d->J);
     if (d->potential.n_obs != 5 * d->K) return fail(IPMCMC_EINVAL, "n_obs=%d, expected 5*K=%d", d->potential.n_obs, 5 * d->K);
     if (!d->param_mean) return fail(IPMCMC_EINVAL, "NULL param_mean");
@@ -287,7 +306,7 @@ extern "C" int ipmcmc_forward(ipmcmc_problem *p, int64_t n, const double *u_dev,
 // ------------------------------------------------------------------------------------------------
 // sampler
 // ------------------------------------------------------------------------------------------------
-static int make_sampler(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, SamplerDev &S, cudaStream_t st) {
+static int make_sampler(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, SamplerDev &S, int64_t n_chains) {
     const int d = s->dim;
     if (d < 1 || d > IPMCMC_MAX_DIM) return fail(IPMCMC_EINVAL, "dim=%d outside [1,%d]", d, IPMCMC_MAX_DIM);
     if (p->model == IPMCMC_MODEL_BURGERS && d != p->b.d) return fail(IPMCMC_EINVAL, "dim=%d but the forward model takes %d parameters", d, p->b.d);
@@ -298,6 +317,10 @@ static int make_sampler(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, Sampler
     if (s->factor_kind && !s->factor) return fail(IPMCMC_EINVAL, "factor is NULL");
     if (s->accepter == IPMCMC_ACCEPT_RW && !s->prior_chol) return fail(IPMCMC_EINVAL, "ACCEPT_RW needs prior_chol");
     if (s->coef_sched_dev && s->n_sched < 1) return fail(IPMCMC_EINVAL, "empty schedule");
+    // Philox is keyed by the low 32 bits of the global chain id (philox.cuh)
+    if (s->chain_offset < 0 || s->chain_offset + n_chains > (1LL << 32))
+        return fail(IPMCMC_EUNSUPPORTED, "global chain ids must lie in [0, 2^32): chain_offset=%lld n_chains=%lld",
+                    (long long)s->chain_offset, (long long)n_chains);
     memset(&S, 0, sizeof S);
     S.d = d;
     S.proposer = s->proposer;
@@ -309,15 +332,13 @@ static int make_sampler(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, Sampler
     S.coef_w = s->coef_w;
     S.coef_sched = s->coef_sched_dev;
     S.n_sched = s->n_sched;
-    double *fac = p->scratch, *chol = p->scratch + IPMCMC_MAX_DIM * IPMCMC_MAX_DIM;
     if (s->factor_kind) {
-        const size_t nb = sizeof(double) * (s->factor_kind == 1 ? d : d * d);
-        CUDA_TRY(cudaMemcpyAsync(fac, s->factor, nb, cudaMemcpyHostToDevice, st));
-        S.factor = fac;
+        int rc = cached_table(p, s->factor, s->factor_kind == 1 ? (size_t)d : (size_t)d * d, &S.factor);
+        if (rc) return rc;
     }
     if (s->accepter == IPMCMC_ACCEPT_RW) {
-        CUDA_TRY(cudaMemcpyAsync(chol, s->prior_chol, sizeof(double) * d * d, cudaMemcpyHostToDevice, st));
-        S.prior_chol = chol;
+        int rc = cached_table(p, s->prior_chol, (size_t)d * d, &S.prior_chol);
+        if (rc) return rc;
     }
     if (s->has_constraint) {
         if (!s->box_lo || !s->box_hi) return fail(IPMCMC_EINVAL, "constraint box is NULL");
@@ -344,7 +365,7 @@ extern "C" int ipmcmc_run(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, const
     if (p->model == IPMCMC_MODEL_LORENZ && !b->model_state_dev) return fail(IPMCMC_EINVAL, "Lorenz chains need model_state_dev");
     cudaStream_t st = (cudaStream_t)stream;
     SamplerDev S;
-    int rc = make_sampler(p, s, S, st);
+    int rc = make_sampler(p, s, S, n_chains);
     if (rc) return rc;
     ChainBufDev C;
     C.u = b->u_dev;
@@ -408,47 +429,134 @@ extern "C" int ipmcmc_run(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// pooling of per-chain moments: Chan et al. pairwise merge, one CTA, deterministic order
+// pooling of per-chain moments: Chan et al. merge as a fixed tree (deterministic: the tree depends on
+// n_chains only, not on the launch geometry or the SM count)
+//   pass 1: CTA b reduces chains [b*POOL_CHUNK, (b+1)*POOL_CHUNK); blockIdx.y = component j < d, or
+//           d + k for counter k.  Thread t merges its chains t, t+256, ... in order, then the 256 partial
+//           triples are merged by a shuffle-xor tree inside each warp and a sequential pass over the
+//           8 warps -> partial[b][j] = (n, mean_j, M2_j)   (counters: exact int64 sums)
+//   pass 2: one CTA, thread j merges partial[0..n_blocks)[j] in block order.
+// 65 536 chains: 32 CTAs x (d + 6) rows, a few microseconds (the former single-thread-per-component loop
+// took 0.35 ms per 1024 chains).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pool_moments_kernel(long long n_chains, int d, const double *__restrict__ cnt,
-                                                           const double *__restrict__ mean,
-                                                           const double *__restrict__ m2,
-                                                           const long long *__restrict__ counters,
-                                                           double *__restrict__ out) {
-    // thread t < d merges component t over all chains sequentially in chain order (deterministic,
-    // independent of the launch geometry); threads d..d+5 sum the six counters.
-    const int t = threadIdx.x;
-    if (t < d) {
-        double n = 0.0, mu = 0.0, M2 = 0.0;
-        for (long long c = 0; c < n_chains; ++c) {
+constexpr int POOL_THREADS = 256;
+constexpr int POOL_CHUNK = 2048;
+
+struct Mom3 {
+    double n, mean, m2;
+};
+__device__ __forceinline__ Mom3 chan_merge(const Mom3 &a, const Mom3 &b) {
+    const double nt = a.n + b.n;
+    if (!(nt > 0.0)) return Mom3{0.0, 0.0, 0.0};
+    const double delta = b.mean - a.mean;
+    return Mom3{nt, a.mean + delta * (b.n / nt), (a.m2 + b.m2) + delta * delta * (a.n * b.n / nt)};
+}
+
+__global__ void __launch_bounds__(POOL_THREADS) pool_partial_kernel(long long n_chains, int d,
+                                                                    const double *__restrict__ cnt,
+                                                                    const double *__restrict__ mean,
+                                                                    const double *__restrict__ m2,
+                                                                    const long long *__restrict__ counters,
+                                                                    double *__restrict__ partial_mom,      // [n_blocks, d, 3]
+                                                                    long long *__restrict__ partial_cnt) { // [n_blocks, CNT_N]
+    __shared__ Mom3 smom[POOL_THREADS / 32];
+    __shared__ long long scnt[POOL_THREADS / 32];
+    const int t = threadIdx.x, j = blockIdx.y, lane = t & 31, warp = t >> 5;
+    const long long c0 = (long long)blockIdx.x * POOL_CHUNK;
+    const long long c1 = c0 + POOL_CHUNK < n_chains ? c0 + POOL_CHUNK : n_chains;
+    if (j < d) {
+        Mom3 acc{0.0, 0.0, 0.0};
+        for (long long c = c0 + t; c < c1; c += POOL_THREADS) {
             const double nb = cnt[c];
-            if (nb <= 0.0) continue;
-            const double mb = mean[c * d + t], Mb = m2[c * d + t];
-            const double nt = n + nb, delta = mb - mu;
-            mu += delta * (nb / nt);
-            M2 += Mb + delta * delta * (n * nb / nt);
-            n = nt;
+            if (nb > 0.0) acc = chan_merge(acc, Mom3{nb, mean[c * d + j], m2[c * d + j]});
         }
-        out[1 + t] = mu;
-        out[1 + d + t] = M2;
-        if (t == 0) out[0] = n;
-    } else if (t < d + CNT_N) {
-        const int k = t - d;
-        long long s = 0;
-        for (long long c = 0; c < n_chains; ++c) s += counters[c * CNT_N + k];
-        out[1 + 2 * d + k] = (double)s;
+#pragma unroll
+        for (int off = 1; off < 32; off *= 2) {
+            Mom3 o{__shfl_xor_sync(FULL, acc.n, off), __shfl_xor_sync(FULL, acc.mean, off), __shfl_xor_sync(FULL, acc.m2, off)};
+            acc = (lane & off) ? chan_merge(o, acc) : chan_merge(acc, o);   // lower lane first: same bits on both
+        }
+        if (lane == 0) smom[warp] = acc;
+        __syncthreads();
+        if (t == 0) {
+            Mom3 r = smom[0];
+            for (int w = 1; w < POOL_THREADS / 32; ++w) r = chan_merge(r, smom[w]);
+            double *o = partial_mom + ((long long)blockIdx.x * d + j) * 3;
+            o[0] = r.n;
+            o[1] = r.mean;
+            o[2] = r.m2;
+        }
+    } else {
+        const int k = j - d;
+        long long sum = 0;
+        for (long long c = c0 + t; c < c1; c += POOL_THREADS) sum += counters[c * CNT_N + k];
+#pragma unroll
+        for (int off = 16; off > 0; off /= 2) sum += __shfl_xor_sync(FULL, sum, off);
+        if (lane == 0) scnt[warp] = sum;
+        __syncthreads();
+        if (t == 0) {
+            long long r = 0;
+            for (int w = 0; w < POOL_THREADS / 32; ++w) r += scnt[w];
+            partial_cnt[(long long)blockIdx.x * CNT_N + k] = r;
+        }
     }
+}
+
+__global__ void __launch_bounds__(64) pool_final_kernel(int n_blocks, int d, const double *__restrict__ partial_mom,
+                                                        const long long *__restrict__ partial_cnt,
+                                                        double *__restrict__ out) {
+    for (int j = threadIdx.x; j < d + CNT_N; j += blockDim.x) {
+        if (j < d) {
+            Mom3 r{0.0, 0.0, 0.0};
+            for (int b = 0; b < n_blocks; ++b) {
+                const double *p = partial_mom + ((long long)b * d + j) * 3;
+                r = chan_merge(r, Mom3{p[0], p[1], p[2]});
+            }
+            out[1 + j] = r.mean;
+            out[1 + d + j] = r.m2;
+            if (j == 0) out[0] = r.n;
+        } else {
+            long long sum = 0;
+            for (int b = 0; b < n_blocks; ++b) sum += partial_cnt[(long long)b * CNT_N + (j - d)];
+            out[1 + 2 * d + (j - d)] = (double)sum;
+        }
+    }
+}
+
+extern "C" int64_t ipmcmc_pool_scratch_bytes(int64_t n_chains, int32_t dim) {
+    const long long nb = (n_chains + POOL_CHUNK - 1) / POOL_CHUNK;
+    return (int64_t)(nb * (3LL * dim * sizeof(double) + CNT_N * sizeof(long long)));
+}
+
+static int pool_launch(long long n_chains, int d, const double *cnt, const double *mean, const double *m2,
+                       const long long *counters, double *pooled, void *scratch, cudaStream_t st) {
+    const long long nb = (n_chains + POOL_CHUNK - 1) / POOL_CHUNK;
+    if (nb > 65535LL * 1024) return fail(IPMCMC_EUNSUPPORTED, "n_chains=%lld too large to pool", n_chains);
+    double *pmom = (double *)scratch;
+    long long *pcnt = (long long *)(pmom + nb * 3 * d);
+    pool_partial_kernel<<<dim3((unsigned)nb, (unsigned)(d + CNT_N)), POOL_THREADS, 0, st>>>(n_chains, d, cnt, mean, m2, counters, pmom, pcnt);
+    CUDA_TRY(cudaGetLastError());
+    pool_final_kernel<<<1, 64, 0, st>>>((int)nb, d, pmom, pcnt, pooled);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int ipmcmc_pool_moments(int64_t n_chains, int32_t dim, const double *mom_count_dev,
                                    const double *mom_mean_dev, const double *mom_m2_dev, const int64_t *counters_dev,
-                                   double *pooled_dev, void *stream) {
+                                   double *pooled_dev, void *scratch_dev, int64_t scratch_bytes, void *stream) {
     if (dim < 1 || dim > IPMCMC_MAX_DIM) return fail(IPMCMC_EINVAL, "dim=%d", dim);
+    if (n_chains < 1) return fail(IPMCMC_EINVAL, "n_chains=%lld", (long long)n_chains);
     if (!mom_count_dev || !mom_mean_dev || !mom_m2_dev || !counters_dev || !pooled_dev) return fail(IPMCMC_EINVAL, "NULL argument");
-    pool_moments_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(n_chains, dim, mom_count_dev, mom_mean_dev, mom_m2_dev,
-                                                             (const long long *)counters_dev, pooled_dev);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
+    const int64_t need = ipmcmc_pool_scratch_bytes(n_chains, dim);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (scratch_dev) {
+        if (scratch_bytes < need) return fail(IPMCMC_EINVAL, "pool scratch: %lld bytes given, %lld needed", (long long)scratch_bytes, (long long)need);
+        return pool_launch(n_chains, dim, mom_count_dev, mom_mean_dev, mom_m2_dev, (const long long *)counters_dev, pooled_dev, scratch_dev, st);
+    }
+    void *tmp = nullptr;   // no caller scratch: stream-ordered allocation
+    CUDA_TRY(cudaMallocAsync(&tmp, (size_t)need, st));
+    const int rc = pool_launch(n_chains, dim, mom_count_dev, mom_mean_dev, mom_m2_dev, (const long long *)counters_dev, pooled_dev, tmp, st);
+    cudaFreeAsync(tmp, st);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -458,36 +566,52 @@ __global__ void fill_kernel(double *p, long long n, double v) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 
+static bool uses_queue(const ipmcmc_problem *p) { return p->model == IPMCMC_MODEL_LORENZ || p->b.N <= 1024; }
+
 extern "C" int ipmcmc_sample_host(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, int64_t n_chains, int64_t n_steps,
-                                  const double *u0_host, double *model_state_host, double *samples_host,
-                                  int64_t n_record, int64_t *counters_host, double *pooled_host, void *stream) {
-    if (!p || !s || !u0_host) return fail(IPMCMC_EINVAL, "NULL argument");
-    if (n_chains <= 0) return fail(IPMCMC_EINVAL, "n_chains=%lld", (long long)n_chains);
-    cudaStream_t st = (cudaStream_t)stream;
+                                  const ipmcmc_host_io *io, void *stream) {
+    if (!p || !s || !io || !io->u0_host) return fail(IPMCMC_EINVAL, "NULL argument");
+    if (n_chains <= 0 || n_steps < 0) return fail(IPMCMC_EINVAL, "n_chains=%lld n_steps=%lld", (long long)n_chains, (long long)n_steps);
     const int d = s->dim;
+    const int d_model = p->model == IPMCMC_MODEL_LORENZ ? 3 : p->b.d;
+    if (d < 1 || d > IPMCMC_MAX_DIM || d != d_model) return fail(IPMCMC_EINVAL, "dim=%d but the forward model takes %d parameters", d, d_model);
+    if (io->n_record < 0) return fail(IPMCMC_EINVAL, "n_record=%lld", (long long)io->n_record);
+    cudaStream_t st = (cudaStream_t)stream;
     const size_t B = (size_t)n_chains;
     const size_t nvar = p->model == IPMCMC_MODEL_LORENZ ? (size_t)p->l.nvar : 0;
-    if (nvar && !model_state_host) return fail(IPMCMC_EINVAL, "Lorenz needs model_state_host");
-    // one device arena: u | phi | count | mean | m2 | pooled | model_state | trace | counters(int64)
-    const size_t n_trace = samples_host ? B * (size_t)n_record * d : 0;
+    if (nvar && !io->model_state_host) return fail(IPMCMC_EINVAL, "Lorenz needs model_state_host");
+    const bool queue = io->scheduler == 0 && uses_queue(p);
+    // one device arena: u | phi | count | mean | m2 | pooled | model_state | trace | counters | sched | pool scratch
+    const size_t n_trace = io->samples_host ? B * (size_t)io->n_record * d : 0;
     const size_t n_dbl = B * d + B + B + B * d + B * d + (2 * d + 7) + B * nvar + n_trace;
+    const size_t units = p->model == IPMCMC_MODEL_LORENZ ? (B + lorenz_groups(p->l.K) - 1) / lorenz_groups(p->l.K) : B;
+    const size_t n_sched = queue ? (size_t)sched_len((long long)units) : 0;
+    const size_t pool_bytes = (size_t)ipmcmc_pool_scratch_bytes(n_chains, d);
     double *arena = nullptr;
-    CUDA_TRY(cudaMallocAsync((void **)&arena, n_dbl * sizeof(double) + B * CNT_N * sizeof(long long), st));
+    CUDA_TRY(cudaMallocAsync((void **)&arena, n_dbl * sizeof(double) + (B * CNT_N + n_sched) * sizeof(long long) + pool_bytes, st));
     double *u = arena, *phi = u + B * d, *cnt = phi + B, *mean = cnt + B, *m2 = mean + B * d, *pooled = m2 + B * d;
     double *mstate = pooled + (2 * d + 7), *trace = mstate + B * nvar;
-    long long *counters = (long long *)(trace + n_trace);
+    long long *counters = (long long *)(trace + n_trace), *sched = counters + B * CNT_N;
+    void *pool_scratch = (void *)(sched + n_sched);
     int rc = 0;
     auto cleanup = [&](int code) {
         cudaFreeAsync(arena, st);
         return code;
     };
     cudaError_t e;
-    e = cudaMemcpyAsync(u, u0_host, B * d * sizeof(double), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && nvar) e = cudaMemcpyAsync(mstate, model_state_host, B * nvar * sizeof(double), cudaMemcpyHostToDevice, st);
+    e = cudaMemcpyAsync(u, io->u0_host, B * d * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && nvar) e = cudaMemcpyAsync(mstate, io->model_state_host, B * nvar * sizeof(double), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(cnt, 0, (B + 2 * B * d) * sizeof(double), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(counters, 0, B * CNT_N * sizeof(long long), st);
+    if (e == cudaSuccess) {
+        if (io->phi0_host) {   // Phi(u_0) known from a previous call: no extra solve
+            e = cudaMemcpyAsync(phi, io->phi0_host, B * sizeof(double), cudaMemcpyHostToDevice, st);
+        } else {
+            fill_kernel<<<148, 256, 0, st>>>(phi, (long long)B, nan(""));
+            e = cudaGetLastError();
+        }
+    }
     if (e != cudaSuccess) return cleanup(fail(IPMCMC_ECUDA, "host->device staging: %s", cudaGetErrorString(e)));
-    fill_kernel<<<148, 256, 0, st>>>(phi, (long long)B, nan(""));
     ipmcmc_chain_buffers cb;
     memset(&cb, 0, sizeof cb);
     cb.u_dev = u;
@@ -497,16 +621,26 @@ extern "C" int ipmcmc_sample_host(ipmcmc_problem *p, const ipmcmc_sampler_desc *
     cb.mom_mean_dev = mean;
     cb.mom_m2_dev = m2;
     cb.counters_dev = (int64_t *)counters;
-    cb.trace_dev = samples_host ? trace : nullptr;
-    cb.n_record = samples_host ? n_record : 0;
+    cb.trace_dev = io->samples_host ? trace : nullptr;
+    cb.n_record = io->samples_host ? io->n_record : 0;
+    if (queue) {   // the dynamic step scheduler, like ChainBatch (the fast path)
+        cb.sched_dev = (int64_t *)sched;
+        cb.sched_len = (int64_t)n_sched;
+        const int64_t auto_chunk = n_steps / 64 < 1 ? 1 : (n_steps / 64 > 4 ? 4 : n_steps / 64);
+        cb.sched_chunk = io->sched_chunk > 0 ? io->sched_chunk : (int32_t)auto_chunk;
+    }
     rc = ipmcmc_run(p, s, &cb, n_chains, n_steps, stream);
     if (rc) return cleanup(rc);
-    rc = ipmcmc_pool_moments(n_chains, d, cnt, mean, m2, (const int64_t *)counters, pooled, stream);
-    if (rc) return cleanup(rc);
-    if (samples_host) e = cudaMemcpyAsync(samples_host, trace, n_trace * sizeof(double), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && counters_host) e = cudaMemcpyAsync(counters_host, counters, B * CNT_N * sizeof(long long), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && pooled_host) e = cudaMemcpyAsync(pooled_host, pooled, (2 * d + 7) * sizeof(double), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && nvar) e = cudaMemcpyAsync(model_state_host, mstate, B * nvar * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (io->pooled_host) {
+        rc = ipmcmc_pool_moments(n_chains, d, cnt, mean, m2, (const int64_t *)counters, pooled, pool_scratch, (int64_t)pool_bytes, stream);
+        if (rc) return cleanup(rc);
+    }
+    if (io->samples_host) e = cudaMemcpyAsync(io->samples_host, trace, n_trace * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && io->u_host) e = cudaMemcpyAsync(io->u_host, u, B * d * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && io->phi_host) e = cudaMemcpyAsync(io->phi_host, phi, B * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && io->counters_host) e = cudaMemcpyAsync(io->counters_host, counters, B * CNT_N * sizeof(long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && io->pooled_host) e = cudaMemcpyAsync(io->pooled_host, pooled, (2 * d + 7) * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && nvar) e = cudaMemcpyAsync(io->model_state_host, mstate, B * nvar * sizeof(double), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cleanup(fail(IPMCMC_ECUDA, "run/device->host: %s", cudaGetErrorString(e)));
     return cleanup(0);

@@ -146,7 +146,9 @@ __device__ __forceinline__ void lorenz_advance_group(const LorenzDev &P, const S
         const double w = proposal_noise(Sd, C, Gp, cs, cg, s, n_steps, gstep);
         const double vi = ca * ui + cb * w;
         if (C.vlog && own) C.vlog[(c * n_steps + s) * d + L.k] = vi;
-        const bool ok = active && (!Sd.has_constraint || constraint_ok(Sd, Gp, vi));
+        // the box test ballots over the FULL warp: every lane evaluates it, `active` is applied afterwards
+        const bool cok = !Sd.has_constraint || constraint_ok(Sd, Gp, vi);
+        const bool ok = active && cok;
         // The reference evaluates Phi(u) and then Phi(v) every step, each solve starting where
         // the previous one ended (accepter.py:121-122 + lorenz_mcmc.py:66).  One inlined call
         // site serves both passes so the integrator state stays in registers.

@@ -173,7 +173,7 @@ class ChainBatch:
 
     COUNTER_NAMES = ("calls", "accepts", "work_a", "work_b", "nonfinite", "constraint_rejects")
 
-    def __init__(self, problem, u0, n_chains=None, model_state=None, chain_offset=0, scheduler=None):
+    def __init__(self, problem, u0, n_chains=None, model_state=None, chain_offset=0, scheduler=None, phi0=None):
         self.problem = problem
         scheduler = scheduler or os.environ.get("IPMCMC_SCHEDULER", "dynamic")
         dev = problem.device
@@ -195,7 +195,18 @@ class ChainBatch:
             u0_t = u0_t.contiguous().pin_memory()
         self.u = u0_t.to(dev, non_blocking=True).contiguous().clone()
         self.h2d_bytes = self.u.numel() * 8
-        self.phi = torch.full((self.n,), float("nan"), dtype=F64, device=dev)
+        if phi0 is None:
+            # NaN = not evaluated yet: the first launch solves for Phi(u_0)
+            self.phi = torch.full((self.n,), float("nan"), dtype=F64, device=dev)
+        else:
+            # Phi(u_0) known (e.g. `last_run["phi"]` of the run that produced u_0): no extra solve
+            ph = torch.as_tensor(np.asarray(phi0, dtype=np.float64) if not torch.is_tensor(phi0) else phi0, dtype=F64)
+            if ph.numel() != self.n:
+                raise ValueError("phi0 has %d entries, expected %d" % (ph.numel(), self.n))
+            if ph.device.type != "cuda":
+                ph = ph.contiguous().pin_memory()
+            self.phi = ph.reshape(self.n).to(dev, non_blocking=True).contiguous().clone()
+            self.h2d_bytes += self.n * 8
         self.model_state = None
         if problem.kind == _lib.MODEL_LORENZ:
             ms = problem.model.IC if model_state is None else model_state
@@ -214,6 +225,7 @@ class ChainBatch:
         self.counters = torch.zeros((self.n, _lib.N_COUNTERS), dtype=torch.int64, device=dev)
         self.step = 0
         self._keep = []
+        self._pool_scratch = None
         self.launches = 0
         self.placement = None
         self._work_prev = None
@@ -274,10 +286,15 @@ class ChainBatch:
     def pooled(self):
         """Chan-merged moments + counters over this batch: cuda tensor [2d + 7]
         (n, mean[d], M2[d], calls, accepts, work_a, work_b, nonfinite, constraint_rejects)."""
+        lib = self.problem.lib
         out = torch.empty((2 * self.d + 1 + _lib.N_COUNTERS,), dtype=F64, device=self.problem.device)
-        check(self.problem.lib.ipmcmc_pool_moments(self.n, self.d, _ptr(self.mom_count), _ptr(self.mom_mean),
-                                                   _ptr(self.mom_m2), _ptr(self.counters), _ptr(out), _stream()))
-        self.launches += 1
+        if self._pool_scratch is None:
+            nbytes = int(lib.ipmcmc_pool_scratch_bytes(self.n, self.d))
+            self._pool_scratch = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=self.problem.device)
+        check(lib.ipmcmc_pool_moments(self.n, self.d, _ptr(self.mom_count), _ptr(self.mom_mean), _ptr(self.mom_m2),
+                                      _ptr(self.counters), _ptr(out), _ptr(self._pool_scratch),
+                                      self._pool_scratch.numel(), _stream()))
+        self.launches += 2
         return out
 
 

@@ -35,9 +35,28 @@ def windowed_autocorrelation(samples, tau_max):
     return ac / avg_over
 
 
-def uncorrelated_sample_spacing(samples, tau_max=100, threshold=1e-3):
-    """tau_0 of the reference (utilities.py:169-186): first lag at which the variable-averaged
-    windowed autocorrelation drops to <= threshold (tau_max if it never does)."""
+def uncorrelated_sample_spacing(x, threshold=1e-3):
+    """tau_0 of the reference (report/scripts/burgers/utilities.py:169-186), restated faithfully:
+    x [n_vars, n]; the window length tau starts at 10 and grows by x1.5 (truncated) per round; each round
+    averages the windowed autocorrelation (helpers.py:41-54) over the variables and returns the first lag
+    at which it is <= 0.001.  When fewer than two windows of the current tau fit into the chain the
+    reference gives up and returns ``len(x)`` -- the number of VARIABLES, since x is [n_vars, n] (kept)."""
+    x = np.asarray(x)
+    tau = 10
+    while True:
+        if 2 > int(len(x[0, :]) / tau):
+            return len(x)              # "never decorrelate"
+        tau = int(tau * 1.5)
+        avg_ac = np.mean(windowed_autocorrelation(x, tau), axis=0)
+        idx = np.argwhere(avg_ac <= threshold)
+        if len(idx) > 0:
+            return int(idx[0][0])
+
+
+def fixed_window_sample_spacing(samples, tau_max=100, threshold=1e-3):
+    """First lag at which the variable-averaged windowed autocorrelation of ONE window length tau_max
+    drops to <= threshold (tau_max if it never does).  Not the reference's definition (see
+    uncorrelated_sample_spacing): a fixed window makes sweep points comparable."""
     ac = np.mean(windowed_autocorrelation(samples, tau_max), axis=0)
     below = np.nonzero(ac <= threshold)[0]
     return int(below[0]) if below.size else int(tau_max)

@@ -120,7 +120,7 @@ def record_chain(ref, sampler_factory, u0, n_steps, name, extra):
     print(name, "acc", accepter.accepts, "/", accepter.calls)
 
 
-def gen_burgers_chains(ref):
+def gen_burgers_chains(ref, only_n256=False):
     ip = ref.ip_mcmc
     prior = ip.GaussianDistribution(PRIOR_MEAN, PRIOR_STD ** 2 * np.identity(3))
 
@@ -140,6 +140,15 @@ def gen_burgers_chains(ref):
                     ip.CountedAccepter(ip.StandardRWAccepter(rec, prior)), rec)
         return f
 
+    # the benchmark configuration (BASELINE.json configs[2]): 256 cells, pCN beta = 0.25 -- from the
+    # reference's u_0 = 0 (burgers_mcmc.py:129-134), then continued from its last state with a new tape
+    record_chain(ref, pcn(256, 0.25), np.zeros(3), 40, "chain_burgers_pcn_N256.npz",
+                 dict(N=256, beta=0.25, seed=2))
+    cont = np.load(os.path.join(OUT, "chain_burgers_pcn_N256.npz"))["samples"][-1]   # continue where it ended
+    record_chain(ref, pcn(256, 0.25), cont, 150, "chain_burgers_pcn_N256_continued.npz",
+                 dict(N=256, beta=0.25, seed=6))
+    if only_n256:
+        return
     record_chain(ref, pcn(64, 0.25), np.zeros(3), 120, "chain_burgers_pcn_N64.npz",
                  dict(N=64, beta=0.25, seed=2))
     record_chain(ref, pcn(128, 0.15), np.zeros(3), 60, "chain_burgers_pcn_N128.npz",
@@ -317,8 +326,34 @@ def gen_burgers_kl(ref):
         print("burgers_kl", N, m)
 
 
+def gen_tau0(ref):
+    """tau_0 of the reference (utilities.uncorrelated_sample_spacing, utilities.py:169-186, built on
+    helpers.autocorrelation, helpers.py:41-54).  helpers.py cannot be imported (it imports POT and runs a
+    test at import), so the ONE function is compiled from its source file in place (nothing is copied)."""
+    import ast
+    src = open(os.path.join(ref_loader.REFERENCE_ROOT, "report", "scripts", "helpers.py")).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "autocorrelation"]
+    ns = dict(np=np, MCMCSampler=ref.ip_mcmc.MCMCSampler)
+    exec(compile(ast.Module(body=fn, type_ignores=[]), "helpers.py", "exec"), ns)
+    ref.utilities.autocorrelation = ns["autocorrelation"]
+    rng = np.random.default_rng(12)
+    out = {}
+    for i, (n, rho) in enumerate([(1500, 0.9), (1500, 0.5), (400, 0.97), (25, 0.99), (3000, 0.0), (12, 0.9)]):
+        x = np.empty((3, n))
+        e = rng.standard_normal((3, n))
+        x[:, 0] = e[:, 0]
+        for k in range(1, n):
+            x[:, k] = rho * x[:, k - 1] + np.sqrt(1 - rho ** 2) * e[:, k]
+        out[f"case{i}_x"] = x
+        out[f"case{i}_tau0"] = ref.utilities.uncorrelated_sample_spacing(x)
+        out[f"case{i}_ac20"] = ns["autocorrelation"](x, 20) if n >= 20 else np.zeros((3, 20))
+        print("tau0 case", i, n, rho, "->", out[f"case{i}_tau0"])
+    out["n_cases"] = 6
+    np.savez(os.path.join(OUT, "tau0_reference.npz"), **out)
+
+
 GROUPS = dict(burgers=gen_burgers_forward, kl=gen_burgers_kl, chains=gen_burgers_chains, kats=gen_operator_kats,
-              lorenz=gen_lorenz)
+              lorenz=gen_lorenz, tau0=gen_tau0, chains256=lambda ref: gen_burgers_chains(ref, only_n256=True))
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)

@@ -98,6 +98,35 @@ def test_forward_random_parameters_vs_oracle(G, N):
         assert phid[i] == opot(u[i])
 
 
+@pytest.mark.parametrize("N", [33, 64, 128, 256])
+def test_fused_on_boundary_ghost_inputs_with_the_cap_lifted(G, N):
+    """FUSED numerics on the inputs where the reference's interior-only CFL (rusanov.py:102-109) lets a
+    ghost cell sampled from the initial condition (rusanov.py:32) overshoot in the FIRST time step:
+    u = [0.3, -0.2, -0.49] has an all-positive initial condition (ghost 2.8, interior 0.05) and a
+    sign-changing state after step 1 (min u ~ -4e3 at 64 cells).  The select-free positive loop may only be
+    entered on the state AFTER the peeled first step (burgers.cuh: state_positive); with the safety cap
+    lifted the FUSED solve must follow the reference through the blow-up: same FV step count, G and Phi
+    within the north-star tolerance."""
+    rng = np.random.default_rng(100 + N)
+    u = np.concatenate([[[0.3, -0.2, -0.49], [0.3, -0.2, 1.49], [0.3, 0.2, -0.49], [-0.2, -0.3, -0.495]],
+                        np.column_stack([0.25 * rng.standard_normal(8), 0.25 * rng.standard_normal(8),
+                                         rng.choice([-0.5, 1.5], 8) + 0.02 * rng.standard_normal(8)])])
+    P = B.BurgersProblem(N)
+    fe, pe, _, y = G.burgers_setup(N, "exact", max_fv_steps=10 ** 7)
+    ff, pf, _, _ = G.burgers_setup(N, "fused", y=y, max_fv_steps=10 ** 7)
+    opot = O.Potential(P, y, G.NOISE_COV)
+    re_ = pe.problem().forward(u, want_state=True)
+    rf = pf.problem().forward(u, want_state=True)
+    we, wf = re_["work"][:, 0].cpu().numpy(), rf["work"][:, 0].cpu().numpy()
+    Ge, Gf, phe, phf = (t.cpu().numpy() for t in (re_["G"], rf["G"], re_["phi"], rf["phi"]))
+    assert we.max() > 20 * N                                   # at least one blow-up solve in the batch
+    for i in (0, 3):                                           # EXACT is the reference bit for bit, also here
+        assert np.array_equal(Ge[i], P.G(u[i])) and we[i] == P.last_n_fv and phe[i] == opot(u[i])
+    assert np.array_equal(wf, we)                              # identical step counts
+    np.testing.assert_allclose(Gf, Ge, rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(phf, phe, rtol=RTOL)
+
+
 def test_callable_interfaces_match_reference_semantics(G):
     """observation_operator(u) -> ndarray[q]; potential(u) -> float (potential.py:53-54)."""
     g = golden("burgers_forward_N64.npz")

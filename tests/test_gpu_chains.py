@@ -28,24 +28,43 @@ def _spec(kind, g, prior, **kw):
                          prior_chol=prior.L, **kw)
 
 
+NUMERICS = ["exact", "fused"]
+
+
+def _check_phi(numerics, got, want):
+    """EXACT: bit-identical; FUSED (the numerics bench.py measures): north-star tolerance 1e-10 relative."""
+    if numerics == "exact":
+        assert np.array_equal(got, want)
+    else:
+        np.testing.assert_allclose(got, want, rtol=1e-10)
+
+
+@pytest.mark.parametrize("numerics", NUMERICS)
 @pytest.mark.parametrize("name,kind", [("chain_burgers_pcn_N64.npz", "pcn"), ("chain_burgers_pcn_N128.npz", "pcn"),
-                                       ("chain_burgers_rw_N64.npz", "rw")])
-def test_replay_reference_chain(G, name, kind):
+                                       ("chain_burgers_rw_N64.npz", "rw"),
+                                       ("chain_burgers_pcn_N256.npz", "pcn"),              # the bench grid, from u_0 = 0
+                                       ("chain_burgers_pcn_N256_continued.npz", "pcn")])   # ... and 150 steps further on
+def test_replay_reference_chain(G, name, kind, numerics):
+    """The reference's own chain (MCMCSampler.run with a noise tape, oracle/make_golden.py) replayed with
+    the tape injected: every proposal, every accept decision (hence every state) and every Phi(v)."""
     g = golden(name)
-    f, pot, prior, _ = G.burgers_setup(int(g["N"]))
+    f, pot, prior, _ = G.burgers_setup(int(g["N"]), numerics)
     states, slog, vlog, ch = G.run_injected(pot, _spec(kind, g, prior), g["u0"], g["normals"], g["uniforms"], n_copies=3)
+    acc_ref = np.all(g["samples"] == g["v"], axis=1)
     for c in range(3):
-        assert np.array_equal(states[c], g["samples"])
+        assert np.array_equal(states[c], g["samples"])                 # all accept decisions
         assert np.array_equal(vlog[c], g["v"])
-        assert np.array_equal(slog[c, :, 0], g["phi_v"])
-        assert int(slog[c, :, 2].sum()) == int(g["accepts"])
+        _check_phi(numerics, slog[c, :, 0], g["phi_v"])
+        assert np.array_equal(slog[c, :, 2].astype(bool), acc_ref) and int(slog[c, :, 2].sum()) == int(g["accepts"])
     cnt = ch.counters.cpu().numpy()
     assert np.all(cnt[:, 0] == int(g["calls"])) and np.all(cnt[:, 1] == int(g["accepts"]))
     assert np.all(cnt[:, 3] == len(g["normals"]) + 1)      # one solve per step + Phi(u_0)
     # accept probabilities vs the oracle's exp (device exp is <= 1 ulp from libm)
-    a_ref = np.exp(g["phi_u"] - g["phi_v"]) if kind == "pcn" else None
-    if a_ref is not None:
-        np.testing.assert_allclose(slog[0, :, 1], a_ref, rtol=1e-14)
+    if kind == "pcn":
+        a_ref = np.exp(g["phi_u"] - g["phi_v"])
+        np.testing.assert_allclose(slog[0, :, 1], a_ref, rtol=1e-14 if numerics == "exact" else 1e-6, atol=1e-300)
+        # no decision of this tape is borderline at the FUSED tolerance: |a - U| >> 1e-10 * a * Phi
+        assert np.min(np.abs(a_ref - g["uniforms"]) / np.maximum(a_ref, 1e-300)) > 1e-6
 
 
 def test_recompute_phi_u_is_bit_equivalent_for_burgers(G):
@@ -59,25 +78,28 @@ def test_recompute_phi_u_is_bit_equivalent_for_burgers(G):
     assert c2.counters[0, 3].item() == 2 * len(g["normals"]) + 1   # the reference's 2 solves per step
 
 
-def test_replay_varstep_schedule(G):
+@pytest.mark.parametrize("numerics", NUMERICS)
+def test_replay_varstep_schedule(G, numerics):
     """VarStepStandardRWProposer with the PWLinear schedule (proposer.py:33-56, burgers_beta.py:131-147)."""
     import ip_mcmc_b200 as M
     from ip_mcmc_b200 import _lib
     g = golden("chain_burgers_varstep_rw_N64.npz")
-    f, pot, prior, _ = G.burgers_setup(64)
+    f, pot, prior, _ = G.burgers_setup(64, numerics)
     sched = np.stack([np.ones(len(g["schedule"])), np.sqrt(2) * np.sqrt(g["schedule"])], axis=1)
     spec = M.SamplerSpec(3, _lib.PROPOSE_RW, _lib.ACCEPT_RW, schedule=sched, prior_chol=prior.L)
     states, slog, _, ch = G.run_injected(pot, spec, g["u0"], g["normals"], g["uniforms"])
     assert np.array_equal(states[0], g["samples"])
+    _check_phi(numerics, slog[0, :, 0], g["phi_v"])
     assert ch.counters[0, 1].item() == int(g["accepts"])
 
 
-def test_replay_constrained_chain(G):
+@pytest.mark.parametrize("numerics", NUMERICS)
+def test_replay_constrained_chain(G, numerics):
     """ConstrainAccepter: a violated box rejects WITHOUT consuming a uniform (accepter.py:52-55)."""
     import ip_mcmc_b200 as M
     from ip_mcmc_b200 import _lib
     g = golden("chain_burgers_constrained_rw_N64.npz")
-    f, pot, prior, _ = G.burgers_setup(64)
+    f, pot, prior, _ = G.burgers_setup(64, numerics)
     lo, hi = float(g["lo"]), float(g["hi"])
     box = M.BoxConstraint([-np.inf, -np.inf, lo], [np.inf, np.inf, hi], shift=[0, 0, -0.5])
     # expand the tape: the reference drew U only on the steps whose proposal satisfied the box
@@ -196,33 +218,35 @@ def test_free_running_chain_statistics_vs_cpu_oracle(G):
 
 
 def test_host_buffer_entry_point_matches_device_path(G):
-    """ipmcmc_sample_host (host pointers in/out, copies inside) == MCMCSampler.run on the same seed."""
-    import ctypes as C
+    """ipmcmc_sample_host (host pointers in/out, copies inside; MCMCSampler.run_host) == MCMCSampler.run on
+    the same seed -- samples, counters, pooled moments, final states -- with the dynamic scheduler and the
+    static map, and continued from a known Phi(u_0) without the extra solve."""
     import ip_mcmc_b200 as M
-    from ip_mcmc_b200 import _lib
-    f, pot, prior, _ = G.burgers_setup(32)
-    s = M.MCMCSampler(M.ConstSteppCNProposer(0.25, prior), M.CountedAccepter(M.pCNAccepter(pot)), np.random.default_rng(4))
+    f, pot, prior, _ = G.burgers_setup(32, "fused")
+    mk = lambda: M.MCMCSampler(M.ConstSteppCNProposer(0.25, prior), M.CountedAccepter(M.pCNAccepter(pot)), np.random.default_rng(4))
     n_chains, n = 9, 25
+    s = mk()
     ref = s.run(np.zeros(3), n, 0, 1, n_chains=n_chains)
-    spec, _, _ = M.MCMCSampler(M.ConstSteppCNProposer(0.25, prior), M.CountedAccepter(M.pCNAccepter(pot)),
-                               np.random.default_rng(4))._compile(n, 0, 1, None)
-    assert spec.seed == s.last_run["seed"]
-
-    class FakeChains:       # c_desc only needs these attributes
-        _keep, chain_offset, step, problem = [], 0, 0, pot.problem()
-    desc = spec.c_desc(FakeChains, n)
-    u0 = np.zeros((n_chains, 3))
-    samples = np.empty((n_chains, n, 3))
-    counters = np.zeros((n_chains, 6), dtype=np.int64)
-    pooled = np.empty(2 * 3 + 7)
-    lib = _lib.load()
-    _lib.check(lib.ipmcmc_sample_host(pot.problem().handle, C.byref(desc), n_chains, n, _lib.as_double_p(u0), None,
-                                      _lib.as_double_p(samples), n, counters.ctypes.data_as(_lib.c_int64_p),
-                                      _lib.as_double_p(pooled), None))
-    assert np.array_equal(samples, ref)
-    assert counters[:, 0].sum() == n_chains * n and counters[:, 1].sum() == s.last_run["counters"]["accepts"]
-    assert pooled[0] == n_chains * n
-    np.testing.assert_allclose(pooled[1:4], ref.reshape(-1, 3).mean(0), rtol=1e-12)
+    for sched in ("dynamic", "static"):
+        h = mk()
+        got = h.run_host(np.zeros(3), n, 0, 1, n_chains=n_chains, scheduler=sched)
+        assert h.last_run["seed"] == s.last_run["seed"]
+        assert np.array_equal(got, ref)
+        assert np.array_equal(h.last_run["per_chain_counters"], s.last_run["per_chain_counters"].cpu().numpy())
+        assert h.accepter.calls == n_chains * n and h.accepter.accepts == s.accepter.accepts
+        assert h.last_run["pooled_count"] == n_chains * n
+        np.testing.assert_allclose(h.last_run["pooled_mean"], ref.reshape(-1, 3).mean(0), rtol=1e-12)
+        np.testing.assert_allclose(h.last_run["pooled_var"], ref.reshape(-1, 3).var(0, ddof=1), rtol=1e-10)
+        assert np.array_equal(h.last_run["u"], ref[:, -1]) and np.array_equal(h.last_run["phi"], s.last_run["phi"].cpu().numpy())
+    # continuation with a known Phi(u_0): one solve per step, none for u_0; same as the device path
+    a, b = mk(), mk()
+    ra = a.run(s.last_run["u"], 10, 0, 1, phi_0=s.last_run["phi"])
+    rb = b.run_host(h.last_run["u"], 10, 0, 1, phi_0=h.last_run["phi"])
+    assert np.array_equal(ra, rb)
+    assert a.last_run["counters"]["work_b"] == n_chains * 10 == b.last_run["counters"]["work_b"]
+    c = mk()
+    rc = c.run(s.last_run["u"], 10, 0, 1)
+    assert np.array_equal(rc, ra) and c.last_run["counters"]["work_b"] == n_chains * 11
 
 
 def test_placement_does_not_change_results(G):

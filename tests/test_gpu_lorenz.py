@@ -145,15 +145,17 @@ def test_stateful_operator_and_potential_semantics(G):
         np.testing.assert_allclose(pot2(u), opot2(u), rtol=1e-9)
 
 
-def test_long_solves_statistically(G):
+@pytest.mark.parametrize("numerics", ["exact", "fused"])
+def test_long_solves_statistically(G, numerics):
     """T = 20 (the reference's setting): G(u) is a noisy time average; device and reference
-    realisations must agree within the natural variability, and step counts within a few %."""
+    realisations must agree within the natural variability, and step counts within a few %.
+    FUSED is what bench.py measures."""
     gs = golden("lorenz_solves.npz")
     for i in range(int(gs["n_cases"])):
         T = float(gs[f"case{i}_T"])
         if T < 20:
             continue
-        f, pot, _, p = _lorenz_setup(T)
+        f, pot, _, p = _lorenz_setup(T, numerics=numerics)
         n = 64
         ic = p["IC"] + 1e-9 * np.random.default_rng(i).standard_normal((n, 30))   # decorrelated realisations
         r = f.batch(np.tile(gs[f"case{i}_u"], (n, 1)), ic)
@@ -212,3 +214,50 @@ def test_lorenz_dynamic_scheduler_bit_identical_to_static(G, n_chains, n_samples
     assert torch.equal(ca.counters, cb.counters) and torch.equal(ca.u, cb.u) and torch.equal(ca.phi, cb.phi)
     assert torch.equal(ca.mom_count, cb.mom_count) and torch.equal(ca.mom_mean, cb.mom_mean) and torch.equal(ca.mom_m2, cb.mom_m2)
     assert a.accepter.calls == b.accepter.calls and a.accepter.accepts == b.accepter.accepts
+
+
+@pytest.mark.parametrize("numerics", ["exact", "fused"])
+@pytest.mark.parametrize("n_chains", [7, 13])
+def test_lorenz_box_constraint_matches_oracle(G, n_chains, numerics):
+    """ConstrainAccepter on the Lorenz kernels: K = 6 leaves lanes 30, 31 of every warp without a chain and
+    n_chains is not a multiple of the 5 chains a warp holds, so the warp-wide ballot of the box test runs
+    with idle lanes and an idle tail group (all 32 lanes must take part, lorenz_kernels.cuh).  Injected
+    noise; compared with the oracle chain: a violated box rejects without consuming a uniform and without a
+    solve (accepter.py:52-55), every other decision and state equal."""
+    import ip_mcmc_b200 as M
+    from ip_mcmc_b200 import _lib
+    T, n_steps, delta = 0.05, 12, 0.3      # 24 carried solves = 1.2 time units: rounding differences stay ~1e-8
+    f, pot, prior, p = _lorenz_setup(T, numerics=numerics)
+    lo, hi = -1.0, 1.3
+    box = M.BoxConstraint([-np.inf, lo, -np.inf], [np.inf, hi, np.inf], shift=[0.0, 0.0, 0.0])
+    rng = np.random.default_rng(21)
+    u0 = np.array([-0.5, 0.9, 0.2])
+    normals = rng.standard_normal((n_chains, n_steps, 3)) * np.sqrt([10., 1, 10])
+    spec = M.SamplerSpec(3, _lib.PROPOSE_RW, _lib.ACCEPT_RW, coef_u=1.0, coef_w=np.sqrt(2 * delta), prior_chol=prior.L,
+                         constraint=box, recompute_phi_u=True)
+    # oracle chains first: they tell which steps consume a uniform
+    U_dev = np.full((n_chains, n_steps), 0.5)
+    refs = []
+    for c in range(n_chains):
+        op = L.LorenzProblem(6, 4, T, 1, p["prior_means"], p["IC"])
+        opot = O.Potential(op, p["y"], 0.25 * np.diag(p["var"]))
+        tape = rng.random(n_steps)
+        ref = O.run_chain(opot, u0, normals[c], tape, O.RW, O.RW, delta, prior_cov=np.diag([10., 1, 10]),
+                          constraint=lambda v: lo < v[1] < hi, recompute_phi_u=True)
+        valid = ~np.isnan(ref["a"])
+        U_dev[c, valid] = tape[:valid.sum()]
+        refs.append((ref, valid, op))
+    ch = M.ChainBatch(pot.problem(), u0, n_chains=n_chains)
+    trace = torch.empty((n_chains, n_steps, 3), dtype=torch.float64, device="cuda")
+    slog = torch.empty((n_chains, n_steps, 4), dtype=torch.float64, device="cuda")
+    ch.run(spec, n_steps, trace=trace, steplog=slog, inject_w=G.cuda(normals), inject_u=G.cuda(U_dev))
+    states, sl, cnt = trace.cpu().numpy(), slog.cpu().numpy(), ch.counters.cpu().numpy()
+    n_viol = 0
+    for c, (ref, valid, op) in enumerate(refs):
+        assert np.array_equal(states[c], ref["u"]), c
+        assert cnt[c, 0] == n_steps and cnt[c, 1] == ref["accepts"] and cnt[c, 5] == (~valid).sum()
+        assert cnt[c, 2] + cnt[c, 3] == op.n_accepted + op.n_rejected        # no solve on constrained steps
+        np.testing.assert_allclose(sl[c, valid, 0], ref["phi_v"][valid], rtol=1e-6)
+        assert np.all(np.isnan(sl[c, ~valid, 0]))
+        n_viol += (~valid).sum()
+    assert n_viol > 0.1 * n_chains * n_steps                                  # the box actually triggers

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()                       # built by __graft_entry__.build()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.ipmcmc_abi_version() == 1
+    assert lib.ipmcmc_abi_version() == 2
 
 
 def test_ctypes_struct_layout_matches_header_sizes():
@@ -44,6 +44,7 @@ def test_ctypes_struct_layout_matches_header_sizes():
     assert ctypes.sizeof(_lib.LorenzDesc) == 16 + 32 + 8 + 48
     assert ctypes.sizeof(_lib.SamplerDesc) == 32 + 16 + 16 + 40 + 40
     assert ctypes.sizeof(_lib.ChainBuffers) == 18 * 8
+    assert ctypes.sizeof(_lib.HostIO) == 10 * 8
 
 
 def test_argument_validation_without_gpu():
@@ -199,6 +200,21 @@ def test_counted_and_constrain_accepters():
     assert spec["constraint"] is box and spec["kind"] == _lib.ACCEPT_PCN and spec["outer_counted"]
     with pytest.raises(TypeError):
         device_spec(M.ConstrainAccepter(inner, lambda v: True))
+    # nesting decides what a counter sees (accepter.py:20-27, 52-55): inside the ConstrainAccepter it never
+    # sees a constraint-rejected proposal; the device counters are credited accordingly
+    from ip_mcmc_b200.accepter import credit_counters
+    c_in, c_out = M.CountedAccepter(inner), None
+    c_out = M.CountedAccepter(M.ConstrainAccepter(c_in, box))
+    rng = MockRNG(0.3)
+    for v in (1.2, 1.6, 0.9, 1.7, -0.9):                     # 1.6, 1.7 and -0.9 violate -1 < v - 0.5 < 1
+        c_out(np.zeros(1), np.array([v]), rng)
+    assert (c_out.calls, c_out.accepts, c_in.calls, c_in.accepts) == (5, 2, 2, 2)
+    spec = device_spec(c_out)
+    assert [(c is c_out, inside) for c, inside in spec["counted"]][0] == (True, False)
+    assert [(c is c_in, inside) for c, inside in spec["counted"]][1] == (True, True)
+    c_out.reset(), c_in.reset()
+    credit_counters(spec, calls=5, accepts=2, constraint_rejects=3)
+    assert (c_out.calls, c_out.accepts, c_in.calls, c_in.accepts) == (5, 2, 2, 2)
 
 
 def test_burgers_grid_tables_match_reference_fixture():
@@ -223,6 +239,19 @@ def test_stats_autocorr_and_ess():
     assert 14 < tau < 25                                                            # (1+rho)/(1-rho) = 19
     n, mean, m2 = M.stats.merge_moments([(len(a), a.mean(0), ((a - a.mean(0)) ** 2).sum(0)) for a in np.split(x[:4998].reshape(-1, 1), 3)])
     assert n == 4998 and np.allclose(mean, x[:4998].mean()) and np.allclose(m2 / (n - 1), x[:4998].var(ddof=1))
+
+
+def test_tau0_matches_reference_fixture():
+    """stats.uncorrelated_sample_spacing == the reference's utilities.uncorrelated_sample_spacing
+    (utilities.py:169-186) on series generated by oracle/make_golden.py:gen_tau0, incl. the chain that is
+    too short (the reference then returns len(x), the number of variables) and helpers.autocorrelation."""
+    g = golden("tau0_reference.npz")
+    for i in range(int(g["n_cases"])):
+        x = g[f"case{i}_x"]
+        assert M.stats.uncorrelated_sample_spacing(x) == int(g[f"case{i}_tau0"])
+        if x.shape[1] >= 20:
+            assert np.array_equal(M.stats.windowed_autocorrelation(x, 20), g[f"case{i}_ac20"])
+    assert M.stats.uncorrelated_sample_spacing(g["case5_x"]) == 3
 
 
 def test_studies_histogram_cache_and_schedule(tmp_path):
