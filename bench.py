@@ -10,6 +10,9 @@ Metropolis steps (proposal -> forward solve -> Phi -> accept/reject -> moments).
     burgers_pcn_256   configs[2]: Burgers pCN beta=0.25, 1024 chains x 256 cells per GPU   (default)
     burgers_pcn_1024  configs[3]: Burgers pCN, 8192 chains x 1024 cells per GPU (65536 over 8 GPUs)
     lorenz_rw         configs[1]: Lorenz-96 K=6 J=4 T=20, RW delta=0.125, 4096 chains per GPU
+The default run (burgers_pcn_256) also measures the other two as `extra_workloads` (at every N), the same
+workload with the EXACT numerics, a COLD START leg (the reference's u_0 = 0, 5000 steps in one launch, no
+burn-in: burgers_mcmc.py:129-134) and the C entry point with host buffers (`e2e_c_abi`).
 Scaling is weak: the per-GPU batch is fixed, chains are sharded by global chain id, no data-path
 collective; one all-reduce of pooled moments/counters at the end (inside the timed region).
 
@@ -35,7 +38,7 @@ PRIOR_MEAN = np.array([1.5, 0.25, -0.5])
 WORKLOADS = {
     "burgers_pcn_256": dict(model="burgers", N=256, chains=1024, mcmc_steps=200, beta=0.25),
     "burgers_pcn_1024": dict(model="burgers", N=1024, chains=8192, mcmc_steps=4, beta=0.25),
-    "lorenz_rw": dict(model="lorenz", chains=4096, mcmc_steps=8, delta=0.125, T=20.0),
+    "lorenz_rw": dict(model="lorenz", chains=4096, mcmc_steps=32, delta=0.125, T=20.0),
 }
 
 
@@ -79,6 +82,49 @@ def cpu_sample(wl, n_steps, n_workers, u_start):
     return steps / busy, busy, wall, res
 
 
+def cpu_acceptance(res):
+    return sum(r[2] for r in res) / max(1, sum(r[1] for r in res))
+
+
+def cpu_sample_c(wl, n_steps, n_threads, u_start):
+    """The same chains through the plain-C restatement (oracle/oracle_c.c; 2 forward solves per step like the
+    reference), one chain per host thread.  A much faster CPU figure than the NumPy port, reported beside it."""
+    from oracle import c_oracle as CO, burgers_np as B
+    rng = np.random.default_rng(1000)
+    U = rng.random((n_threads, n_steps))
+    if wl["model"] == "burgers":
+        P = CO.BurgersC(wl["N"], y=B.BurgersProblem(wl["N"]).G_params(TRUTH), noise_cov=0.05 ** 2 * np.identity(5))
+        z = 0.25 * rng.standard_normal((n_threads, n_steps, 3))
+        t0 = time.perf_counter()
+        r = P.run_chains(u_start, z, U, CO.PCN, CO.PCN, wl["beta"], recompute_phi_u=True, n_threads=n_threads)
+    else:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "lorenz_problem_K6_J4.npz"))
+        L = CO.LorenzC(6, 4, wl["T"], 1.0, g["prior_means"], y=g["y"], noise_cov=0.25 * np.diag(g["var"]))
+        z = rng.standard_normal((n_threads, n_steps, 3)) * np.sqrt([10., 1, 10])
+        t0 = time.perf_counter()
+        r = L.run_chains(g["u0"], g["IC"], z, U, CO.RW, CO.RW, wl["delta"], prior_cov=np.diag([10., 1, 10]), n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    return n_threads * n_steps / dt, dt, float(r["accepted"].mean())
+
+
+def cpu_baselines(wl, cores):
+    """cpu_baseline (NumPy port, the contract's key) and cpu_baseline_c (plain-C port) of one workload."""
+    n = cpu_steps_for(wl)
+    v, busy, wall, res = cpu_sample(wl, n, cores, posterior_start(wl))
+    out = dict(cpu_baseline=dict(value=v, unit="chain-steps/s", cores=cores, kind="port", acceptance=cpu_acceptance(res),
+                                 sample="%d processes x %d chain-steps of the same workload, NumPy restatement of the "
+                                        "reference sampler (2 forward solves per step), %.1f s" % (cores, n, busy)))
+    try:
+        n_c = {"burgers": 1500 if wl.get("N", 0) <= 256 else 40, "lorenz": 60}[wl["model"]]
+        vc, dtc, acc_c = cpu_sample_c(wl, n_c, cores, posterior_start(wl))
+        out["cpu_baseline_c"] = dict(value=vc, unit="chain-steps/s", cores=cores, kind="port (plain C, oracle/oracle_c.c)",
+                                     acceptance=acc_c, sample="%d threads x %d chain-steps, 2 forward solves per step, %.1f s"
+                                                              % (cores, n_c, dtc))
+    except Exception as e:      # the C oracle is test infrastructure: never let it break the bench line
+        out["cpu_baseline_c"] = dict(unavailable=str(e)[:200])
+    return out
+
+
 def cpu_steps_for(wl):
     # bounded sample: ~10 s of work per process at N = 256 (~70 chain-steps/s/core), ~15 s at N = 1024, ~12 s Lorenz
     return {"burgers": 600 if wl.get("N", 0) <= 256 else 12, "lorenz": 2}[wl["model"]]
@@ -103,33 +149,38 @@ def run_reference(args, wl, name, out_fd):
     for _ in range(args.warmup if args.warmup < 2 else 1):      # process start-up / import warm-up
         cpu_sample(wl, 1, cores, u_start)
     t_busy = 0.0
-    steps = 0
+    steps = accepts = 0
     for _ in range(args.steps):
         v, busy, wall, res = cpu_sample(wl, n, cores, u_start)
         t_busy += busy
         steps += sum(r[1] for r in res)
+        accepts += sum(r[2] for r in res)
     value = steps / t_busy
     sample = "%d processes x %d chain-steps per bench step (NumPy restatement, 2 forward solves per step as in the reference)" % (cores, n)
     line = dict(impl="reference", metric="chain_steps_per_sec", value=value, unit="chain-steps/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * t_busy / max(args.steps, 1),
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=workload_config(wl, name, args),
-                cpu_baseline=dict(value=value, unit="chain-steps/s", cores=cores, kind="port", sample=sample),
+                acceptance_rate=accepts / max(steps, 1),
+                cpu_baseline=dict(value=value, unit="chain-steps/s", cores=cores, kind="port", sample=sample,
+                                  acceptance=accepts / max(steps, 1)),
                 e2e=dict(value=value, unit="chain-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line, out_fd)
 
 
-def workload_config(wl, name, args):
+def workload_config(wl, name, args, burn_in=None, start=None):
     cfg = dict(workload=name, chains_per_gpu=wl["chains"], mcmc_steps_per_launch=wl["mcmc_steps"])
+    numerics = wl.get("numerics", args.numerics)
     if wl["model"] == "burgers":
         cfg.update(cells=wl["N"], proposer="pCN", beta=wl["beta"], T=1.0, prior="N(u_p, 0.25^2 I_3)",
-                   noise_std=0.05, numerics=args.numerics)
+                   noise_std=0.05, numerics=numerics)
+        cfg["untimed_burn_in_steps"] = args.burn_in if burn_in is None else burn_in
+        cfg["start"] = start or "u* - prior mean (posterior region), then the untimed burn-in"
     else:
         cfg.update(K=6, J=4, T=wl["T"], proposer="RW", delta=wl["delta"], solves_per_step=2,
-                   rtol=1e-3, atol=1e-6, numerics=args.numerics)
-    cfg["untimed_burn_in_steps"] = args.burn_in if wl["model"] == "burgers" else 0
-    if wl["model"] == "burgers":
-        cfg["start"] = "u* - prior mean (posterior region), then the untimed burn-in"
+                   rtol=1e-3, atol=1e-6, numerics=numerics)
+        cfg["untimed_burn_in_steps"] = 0
+        cfg["start"] = "the reference's u_0 = (-1.9, 1.9, 0.9) and IC (lorenz_mcmc.py:139), warm-up launches only"
     cfg["l2"] = "flushed between timed launches (256 MiB memset, untimed); working set << L2 anyway"
     cfg["parallelism"] = "chains sharded by global id, dp%d" % args.gpus
     return cfg
@@ -255,9 +306,13 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_ghz = torch.cuda.get_device_properties(dev).clock_rate / 1e6 if hasattr(torch.cuda.get_device_properties(dev), "clock_rate") else 1.965
+    nominal_fp64 = n_sm * 64 * 2 * 1.965e9 / 1e12      # 64 DFMA lanes per SM per clock at clocks.max.sm
+
     def measure(wl, K, W, with_e2e=True, trace_chains=64, burn_in=0, start=None):
         B, S = wl["chains"], wl["mcmc_steps"]
-        pot, proposer, accepter, u0 = build_problem(M, wl, args.numerics)
+        pot, proposer, accepter, u0 = build_problem(M, wl, wl.get("numerics", args.numerics))
         sampler = M.MCMCSampler(proposer, accepter, np.random.default_rng(2))
         spec, pot, a = sampler._compile(10 ** 9, 0, 1, None)
         problem = pot.problem()
@@ -279,6 +334,8 @@ def main():
         if world > 1:
             parallel.allreduce_pooled(chains.pooled(), 3)   # warm NCCL with the message of the final reduce
             dist.barrier()
+        else:
+            chains.pooled()
         torch.cuda.synchronize()
         sampler_clk.start()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K + 1)]
@@ -294,7 +351,7 @@ def main():
         pooled_local = chains.pooled()
         ev_mid = torch.cuda.Event(enable_timing=True)
         ev_mid.record()
-        pooled = parallel.allreduce_pooled(pooled_local, 3)  # the only collective of the job
+        pooled = parallel.allreduce_pooled(pooled_local, 3)  # the only collective of the job (one all-gather)
         ev[K][1].record()
         torch.cuda.synchronize()
         if world > 1:
@@ -334,34 +391,88 @@ def main():
                    hbm_gbs=hbm_bytes / (sum(kern_ms) * 1e-3) / 1e9, counters=dc_all, steps_all=steps_all,
                    acceptance=dc_all[1] / max(dc_all[0], 1), ess_per_sec=ess_per_chain * B * world / (total_ms * 1e-3),
                    ess_per_chain=ess_per_chain, clocks=sampler_clk.summary(), launches=chains.launches - launches0,
-                   pooled=pooled.cpu().numpy(), wall_s=t_wall, mean_work_per_solve=dc_all[2] / max(dc_all[3], 1)
+                   pooled=pooled.cpu().numpy(), wall_s=t_wall, nonfinite=int(dc_all[4]),
+                   mean_work_per_solve=dc_all[2] / max(dc_all[3], 1)
                    if wl["model"] == "burgers" else (dc_all[2] + dc_all[3]) / max(2 * dc_all[0], 1))
         if with_e2e:
-            # end to end through the public API with HOST buffers: numpy u_0 in, numpy samples out
+            # end to end through the public API with HOST buffers: numpy u_0 (and Phi(u_0), known from the run that
+            # produced it) in, numpy samples out.  (1) MCMCSampler.run: torch-managed pinned staging;
+            # (2) MCMCSampler.run_host = the C entry point ipmcmc_sample_host alone (pageable NumPy buffers).
             u_host = chains.u.cpu().numpy()
+            phi_host = None if pot.G.stateful else chains.phi.cpu().numpy()
             ms_host = chains.model_state.cpu().numpy() if chains.model_state is not None else None
             if ms_host is not None:
                 pot.G.IC = ms_host[0]
             out_host = torch.empty((B, S, 3), dtype=F64).pin_memory()        # pinned result buffer, reused
-            sampler.run(u_host, S, 0, 1, n_chains=B, chain_offset=rank * B, out=out_host)   # warm
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            t0 = time.perf_counter()
-            for _ in range(K):
-                samples = sampler.run(u_host, S, 0, 1, n_chains=B, chain_offset=rank * B, out=out_host)
-            torch.cuda.synchronize()
-            dt = parallel.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
+            out_np = np.empty((B, S, 3))
+
+            def timed(fn):
+                fn()                                         # warm
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                t0 = time.perf_counter()
+                for _ in range(K):
+                    fn()
+                torch.cuda.synchronize()
+                return parallel.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
+
+            dt = timed(lambda: sampler.run(u_host, S, 0, 1, n_chains=B, chain_offset=rank * B, out=out_host, phi_0=phi_host))
             out["e2e"] = dict(value=B * S * K * world / (dt * 1e-3), unit="chain-steps/s",
                               h2d_bytes_per_step=int(sampler.last_run["h2d_bytes"]),
-                              d2h_bytes_per_step=int(sampler.last_run["d2h_bytes"]))
+                              d2h_bytes_per_step=int(sampler.last_run["d2h_bytes"]),
+                              path="MCMCSampler.run(host u_0, Phi(u_0)) -> pinned host samples")
+            dt = timed(lambda: sampler.run_host(u_host, S, 0, 1, n_chains=B, chain_offset=rank * B, out=out_np, phi_0=phi_host))
+            out["e2e_c_abi"] = dict(value=B * S * K * world / (dt * 1e-3), unit="chain-steps/s",
+                                    h2d_bytes_per_step=int(sampler.last_run["h2d_bytes"]),
+                                    d2h_bytes_per_step=int(sampler.last_run["d2h_bytes"]),
+                                    path="ipmcmc_sample_host (ctypes, pageable NumPy buffers, arena + copies inside the C call)")
         return out
+
+    def cold_start(wl, total_steps, reps):
+        """The run a user following INTEGRATION.md gets: MCMCSampler.run(u_0 = 0, total_steps, 0, 1) -- ONE
+        launch of `total_steps` Metropolis steps per chain from the reference's start (burgers_mcmc.py:129-134),
+        no burn-in, all states recorded on the device.  `reps` timed repetitions with different seeds."""
+        B = wl["chains"]
+        pot, proposer, accepter, u0 = build_problem(M, wl, args.numerics)
+        ms, fl, nonfinite, steps_fv, solves = [], [], 0, 0.0, 0.0
+        trace = torch.empty((B, total_steps, 3), dtype=F64, device=dev)
+        for r in range(reps + 1):                           # first repetition = warm-up (short)
+            sampler = M.MCMCSampler(proposer, accepter, np.random.default_rng(100 + r))
+            spec, pot, a = sampler._compile(10 ** 9, 0, 1, None)
+            chains = ChainBatch(pot.problem(), np.zeros(3), n_chains=B, chain_offset=rank * B)
+            n = total_steps if r else min(200, total_steps)
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            chains.run(spec, n, trace=trace[:, :n])
+            e1.record()
+            torch.cuda.synchronize()
+            if r == 0:
+                continue
+            c = chains.counters.sum(0).double().cpu().numpy()
+            ms.append(parallel.max_over_ranks(e0.elapsed_time(e1), dev))
+            fl.append(algorithmic_flops(wl, c[2], c[3]) / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+            nonfinite += int(c[4])
+            steps_fv += c[2]
+            solves += c[3]
+        tf = float(np.mean(fl))
+        return dict(chain_steps_per_sec=B * total_steps * reps * world / (sum(ms) * 1e-3), roofline_tflops=tf,
+                    roofline_frac=tf / peak, roofline_frac_nominal=tf / nominal_fp64,
+                    ms_per_run=[round(x, 2) for x in ms], slowest_over_fastest=max(ms) / min(ms),
+                    nonfinite_phi_per_rank=nonfinite, capped_solves_per_rank=nonfinite,
+                    capped_solve_share_of_fv_steps=nonfinite * float(pot.G.effective_max_fv_steps) / max(steps_fv, 1),
+                    max_fv_steps=int(pot.G.effective_max_fv_steps),
+                    mean_fv_steps_per_solve=steps_fv / max(solves, 1),
+                    config=workload_config(wl, args.workload, args, burn_in=0,
+                                           start="u_0 = 0 (the reference's start, burgers_mcmc.py:129-134), %d steps "
+                                                 "in ONE launch, no burn-in, %d repetitions" % (total_steps, reps)))
 
     peak = M.fp64_peak_tflops(5)
     # Burgers: every leg (GPU, CPU baseline, --impl reference) measures the STATIONARY phase: chains start
-    # in the posterior region (u* - prior mean) and burn in untimed.  (From the reference's u_0 = 0 the chains
-    # spend thousands of steps on a transient along the domain edge, where single chains hit the capped
-    # blow-up solves of DESIGN.md section 7 and one straggler chain sets the launch time.)
+    # in the posterior region (u* - prior mean) and burn in untimed.  The `cold_start` leg measures the run from
+    # the reference's u_0 = 0 without any burn-in.
     burn_in, start = (args.burn_in if wl['model'] == 'burgers' else 0), None
     if wl['model'] == 'burgers':
         start = TRUTH - PRIOR_MEAN
@@ -370,13 +481,27 @@ def main():
     args.burn_in = burn_in
     res = measure(wl, args.steps, max(args.warmup, 3), burn_in=burn_in, start=start)
     extra = {}
-    if not args.no_extra and world == 1 and args.workload == "burgers_pcn_256":
-        for name in ("lorenz_rw", "burgers_pcn_1024"):
-            r = measure(dict(WORKLOADS[name]), 3, 3, with_e2e=False, trace_chains=8, burn_in=100 if name.startswith('burgers') else 0,
-                        start=(TRUTH - PRIOR_MEAN) if name.startswith('burgers') else None)
+    cold = None
+    if not args.no_extra and args.workload == "burgers_pcn_256":
+        # the other BASELINE.json configs, at EVERY N (weak scaling: the same per-GPU batch on every rank)
+        plan = [("lorenz_rw", dict(WORKLOADS["lorenz_rw"]), 0, True),
+                ("burgers_pcn_1024", dict(WORKLOADS["burgers_pcn_1024"]), 100, False),
+                ("burgers_pcn_256_exact", dict(WORKLOADS["burgers_pcn_256"], numerics="exact", mcmc_steps=100), 400, False)]
+        for name, w, b_in, e2e in plan:
+            r = measure(w, 3, 3, with_e2e=e2e, trace_chains=8, burn_in=b_in,
+                        start=(TRUTH - PRIOR_MEAN) if w["model"] == "burgers" else None)
             extra[name] = dict(chain_steps_per_sec=r["value"], acceptance=r["acceptance"],
                                roofline_tflops=r["achieved"], roofline_frac=r["achieved"] / peak,
-                               ms_per_step=r["total_ms"] / 3, config=workload_config(WORKLOADS[name], name, args))
+                               roofline_frac_nominal=r["achieved"] / nominal_fp64, ms_per_step=r["total_ms"] / 3,
+                               allreduce_ms=r["red_ms"], pool_moments_ms=r["pool_ms"], nonfinite_phi=r["nonfinite"],
+                               per_rank_ms=dict(columns=["sum_kernel", "final_reduce", "wall_timed_region", "sm_mhz",
+                                                         "n_throttle_reasons", "slowest_launch", "fastest_launch"],
+                                                rows=r["per_rank"]),
+                               config=workload_config(w, name, args, burn_in=b_in))
+            for k in ("e2e", "e2e_c_abi"):
+                if k in r:
+                    extra[name][k] = r[k]
+        cold = cold_start(dict(wl), 5000, 3)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -393,9 +518,9 @@ def main():
     except Exception:
         pass
     roofline = dict(bound="fp64", achieved=res["achieved"], peak=peak, unit="TFLOP/s", frac=res["achieved"] / peak,
-                    traffic=traffic,
+                    traffic=traffic, peak_nominal=nominal_fp64, frac_of_nominal=res["achieved"] / nominal_fp64,
                     peak_source="DFMA micro-benchmark (ipmcmc_fp64_peak) measured in this run; MEASURED_PEAKS.json has "
-                                "no fp64 entry (nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
+                                "no fp64 entry; peak_nominal = %d SM x 64 FMA/clk x 2 x 1.965 GHz" % n_sm,
                     flops_model="29 FLOP per cell per SSPRK2 step x device-counted FV steps" if wl["model"] == "burgers"
                     else "3444 FLOP per RK45 attempt x device-counted attempts",
                     hbm=dict(achieved=res["hbm_gbs"], peak=hbm_peak, unit="GB/s", frac=res["hbm_gbs"] / hbm_peak,
@@ -404,20 +529,22 @@ def main():
                 warmup=max(args.warmup, 3), ms_per_step=res["total_ms"] / args.steps, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=workload_config(wl, args.workload, args), roofline=roofline, e2e=res.get("e2e"),
+                e2e_c_abi=res.get("e2e_c_abi"),
                 gpu_launches=int(res["launches"]), clocks=res["clocks"], ess_per_sec=res["ess_per_sec"],
                 ess_per_chain_in_timed_window=res["ess_per_chain"], acceptance_rate=res["acceptance"],
+                nonfinite_phi=res["nonfinite"],
                 mean_work_per_solve=res["mean_work_per_solve"], allreduce_ms=res["red_ms"], pool_moments_ms=res["pool_ms"],
                 kernel_ms_per_step=[round(x, 3) for x in res["kern_ms"]],
                 per_rank_ms=dict(columns=["sum_kernel", "final_reduce", "wall_timed_region", "sm_mhz", "n_throttle_reasons",
                                           "slowest_launch", "fastest_launch"], rows=res["per_rank"]),
-                posterior_mean=[float(x) for x in res["pooled"][1:4]], extra_workloads=extra)
+                posterior_mean=[float(x) for x in res["pooled"][1:4]], cold_start=cold, extra_workloads=extra)
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        n = cpu_steps_for(wl)
-        v, busy, wall, _ = cpu_sample(wl, n, cores, posterior_start(wl))
-        line["cpu_baseline"] = dict(value=v, unit="chain-steps/s", cores=cores, kind="port",
-                                    sample="%d processes x %d chain-steps of the same workload, NumPy restatement of "
-                                           "the reference sampler (2 forward solves per step), %.1f s" % (cores, n, busy))
+        line.update(cpu_baselines(wl, cores))
+        if not args.no_extra:
+            for name in ("lorenz_rw", "burgers_pcn_1024"):
+                if name in extra:
+                    extra[name].update(cpu_baselines(dict(WORKLOADS[name]), cores))
     emit(line, out_fd)
     if world > 1:
         dist.destroy_process_group()

@@ -83,7 +83,13 @@ typedef struct ipmcmc_potential_desc {
 typedef struct ipmcmc_burgers_desc {
     int32_t n_cells;          /* N interior cells (the solver carries N+2 with ghosts)          */
     int32_t numerics;         /* IPMCMC_NUMERICS_*                                              */
-    int32_t max_fv_steps;     /* safety cap on FV time steps per solve (<=0: 64*N+1024)         */
+    int32_t max_fv_steps;     /* safety cap on FV time steps per solve; <= 0: 8*N + 256.  A solve takes
+                                 T*N*<max|u|> steps (dt = dx/2 / max|u|, domain length 2): the default
+                                 admits states up to |u| ~ 8 (the reference's prior: 2.5 +- 0.25) and
+                                 stops the blow-up solves the reference's interior-only CFL produces
+                                 when the jump falls between a ghost and the first cell centre
+                                 (rusanov.py:102-109; ~300 N steps there).  A capped solve reports
+                                 Phi = NaN: rejected and counted (counters[4])                    */
     int32_t n_params;         /* d = 3 + n_kl_modes: (delta_1, delta_2, sigma, a_1..a_m)        */
     double T;                 /* end time (the last step is NOT clipped, rusanov.py:40-45)      */
     double dx;                /* solver spacing = linspace retstep (rusanov.py:22-25)           */
@@ -266,6 +272,21 @@ typedef struct ipmcmc_host_io {
 
 int ipmcmc_sample_host(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, int64_t n_chains,
                        int64_t n_steps, const ipmcmc_host_io *io, void *stream);
+
+/* --------------------------------------------------------------------------------------------
+ * d-dimensional histogram of recorded samples, ACCUMULATED into hist_dev across calls -- the device half of
+ *   np.histogramdd(chain.T, bins=n_bins, range=intervals)   report/scripts/burgers/burgers_wasserstein_chain.py:182-184,
+ *                                                           burgers_wasserstein_grid.py:205-231
+ * so that a 100 000-step study keeps bins^d counters instead of its samples.
+ *   samples_dev [n, stride] (the first `dim` entries of each row are used; a trace of ipmcmc_run is [., d])
+ *   shift_dev   [dim] added to every sample first (the scripts add the prior mean, chain.py:257-259)
+ *   edges_dev   [dim, bins+1] bin edges per dimension (np.linspace(lo, hi, bins+1)); numpy semantics:
+ *               right-open bins, the last edge belongs to the last bin, outside values are dropped
+ *   hist_dev    [bins^dim] int64 counters, row-major over dimensions, updated with atomic adds
+ * ------------------------------------------------------------------------------------------ */
+int ipmcmc_histogram_accumulate(int64_t n, int32_t dim, int32_t bins, const double *samples_dev,
+                                int64_t stride, const double *shift_dev, const double *edges_dev,
+                                int64_t *hist_dev, void *stream);
 
 /* --------------------------------------------------------------------------------------------
  * Probes used by the parity tests and the roofline measurement

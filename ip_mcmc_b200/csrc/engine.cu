@@ -142,7 +142,7 @@ extern "C" int ipmcmc_burgers_create(const ipmcmc_burgers_desc *d, ipmcmc_proble
     memset(&b, 0, sizeof b);
     b.N = d->n_cells;
     b.d = d->n_params;
-    b.max_fv_steps = d->max_fv_steps > 0 ? d->max_fv_steps : 64 * d->n_cells + 1024;
+    b.max_fv_steps = d->max_fv_steps > 0 ? d->max_fv_steps : 8 * d->n_cells + 256;   // include/ipmcmc.h: max_fv_steps
     b.T = d->T;
     b.dx = d->dx;
     b.half_dx = 0.5 * d->dx;
@@ -410,16 +410,27 @@ extern "C" int ipmcmc_run(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, const
         int dev = 0, n_sm = 148;
         CUDA_TRY(cudaGetDevice(&dev));
         CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        const long long resident = (long long)n_sm * (8 / wpc);
-        long long ctas = (warps + wpc - 1) / wpc;
-        if (ctas > resident) ctas = resident;
+        long long ctas;
+        int qwpc = wpc;
+        if (warps <= 8LL * n_sm) {
+            // one wave: one CTA per SM, ceil(warps / n_SM) warps each -- every SM gets work (820 groups at 4096
+            // chains: 80 SMs with 6 warps, 68 with 5, instead of 137 CTAs of 6 and 11 idle SMs)
+            ctas = warps < n_sm ? warps : n_sm;
+            qwpc = (int)((warps + ctas - 1) / ctas);
+            const int fit = (int)((48 * 1024) / lorenz_smem_bytes(p->l.K));
+            if (qwpc > fit) { qwpc = fit; ctas = (warps + qwpc - 1) / qwpc; }
+        } else {
+            const long long resident = (long long)n_sm * (8 / wpc);
+            ctas = (warps + wpc - 1) / wpc;
+            if (ctas > resident) ctas = resident;
+        }
         int chunk = b->sched_chunk > 0 ? b->sched_chunk : 1;
         if (const char *e = getenv("IPMCMC_SCHED_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;  // experiments
         C.sched = (long long *)b->sched_dev;
         sched_init_kernel<<<(unsigned)((2 * warps + 255) / 256 < 1184 ? (2 * warps + 255) / 256 : 1184), 256, 0, st>>>(C.sched, warps);
         CUDA_TRY(cudaGetLastError());
         LORENZ_DISPATCH(lorenz_chain_queue_kernel, p->l.J, p->l.K, p->numerics,
-                        <<<(int)ctas, 32 * wpc, wpc * lorenz_smem_bytes(p->l.K), st>>>(p->l, S, C, n_chains, n_steps, chunk));
+                        <<<(int)ctas, 32 * qwpc, qwpc * lorenz_smem_bytes(p->l.K), st>>>(p->l, S, C, n_chains, n_steps, chunk));
         return 0;
     }
     LORENZ_DISPATCH(lorenz_chain_kernel, p->l.J, p->l.K, p->numerics,
@@ -557,6 +568,50 @@ extern "C" int ipmcmc_pool_moments(int64_t n_chains, int32_t dim, const double *
     const int rc = pool_launch(n_chains, dim, mom_count_dev, mom_mean_dev, mom_m2_dev, (const long long *)counters_dev, pooled_dev, tmp, st);
     cudaFreeAsync(tmp, st);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// d-dimensional histogram of recorded samples, accumulated across launches (chain-length / grid studies)
+// ------------------------------------------------------------------------------------------------
+// np.histogramdd semantics (numpy/lib/_histograms_impl.py): bin = searchsorted(edges, x, 'right') - 1 per
+// dimension, a value on the last edge belongs to the last bin, values outside [first, last edge] are dropped.
+// `edges` are the caller's (np.linspace) edges, so that the bin of a value on an edge is numpy's.
+__global__ void __launch_bounds__(256) histogram_kernel(long long n, int d, int bins, const double *__restrict__ x,
+                                                        long long stride, const double *__restrict__ shift,
+                                                        const double *__restrict__ edges,
+                                                        unsigned long long *__restrict__ hist) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long flat = 0;
+        bool inside = true;
+        for (int j = 0; j < d; ++j) {
+            const double *e = edges + (long long)j * (bins + 1);
+            const double v = x[i * stride + j] + shift[j];
+            if (!(v >= e[0] && v <= e[bins])) {   // NaN is dropped too
+                inside = false;
+                break;
+            }
+            int k = (int)((v - e[0]) / (e[bins] - e[0]) * bins);
+            k = k < 0 ? 0 : (k > bins - 1 ? bins - 1 : k);
+            while (k > 0 && v < e[k]) --k;                      // exact searchsorted on the given edges
+            while (k < bins - 1 && v >= e[k + 1]) ++k;
+            flat = flat * bins + k;
+        }
+        if (inside) atomicAdd(hist + flat, 1ull);
+    }
+}
+
+extern "C" int ipmcmc_histogram_accumulate(int64_t n, int32_t dim, int32_t bins, const double *samples_dev,
+                                           int64_t stride, const double *shift_dev, const double *edges_dev,
+                                           int64_t *hist_dev, void *stream) {
+    if (dim < 1 || dim > IPMCMC_MAX_DIM || bins < 1) return fail(IPMCMC_EINVAL, "dim=%d bins=%d", dim, bins);
+    if (n < 0 || stride < dim) return fail(IPMCMC_EINVAL, "n=%lld stride=%lld", (long long)n, (long long)stride);
+    if (!samples_dev || !shift_dev || !edges_dev || !hist_dev) return fail(IPMCMC_EINVAL, "NULL argument");
+    if (n == 0) return 0;
+    const long long blocks = (n + 255) / 256;
+    histogram_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+        n, dim, bins, samples_dev, stride, shift_dev, edges_dev, (unsigned long long *)hist_dev);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

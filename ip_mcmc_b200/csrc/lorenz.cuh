@@ -75,6 +75,29 @@ __device__ __forceinline__ double pow_m01(double x) {
     return y;
 }
 
+// FUSED controller: 0.9 * x^(-1/10) for a positive normal x inside the fp32 range, ~5e-13 relative.
+// Seed on the SFU in fp32 WITHOUT the slow F2F conversions or the denormal fix-ups of __log2f/exp2f
+// (x is re-biased into an fp32 bit pattern with two integer instructions, the result widened the same way;
+// lg2/ex2.approx.ftz), then one Newton round y <- y (1 + (1 - x y^10)/10) arranged in 5 dependent levels
+// (y2 | y4, x*y2 | y8 | 1 - (x y2) y8 | fma) with SAFETY folded in.  Garbage in (0, inf, NaN, out of the
+// fp32 range) gives garbage out: the caller overrides those cases by predicates on x.
+__device__ __forceinline__ double rk_factor_fused(double ss, double inv_n, float log2n_10) {
+    // seed straight from the bits of ss = n*e2: (ss/n)^(-1/10) = 2^(-0.1 lg2(ss) + 0.1 lg2(n)), the 1/n as one FFMA
+    const uint32_t hi = (uint32_t)__double2hiint(ss), lo = (uint32_t)__double2loint(ss);
+    const float xf = __uint_as_float(((hi - 0x38000000u) << 3) | (lo >> 29));      // truncated, 2^-23 relative
+    float lg, yf;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(fmaf(lg, -0.1f, log2n_10)));
+    const uint32_t yb = __float_as_uint(yf);
+    const double y = __hiloint2double((int)((yb >> 3) + 0x38000000u), (int)(yb << 29));   // exact widening
+    const double x = ss * inv_n;                                                   // beside the SFU chain
+    const double y2 = y * y, y09 = y * RK_SAFETY, y009 = y * (0.1 * RK_SAFETY);
+    const double y4 = y2 * y2, a = x * y2;
+    const double y8 = y4 * y4;
+    const double r = fma(-a, y8, 1.0);
+    return fma(y009, r, y09);
+}
+
 // SAFETY * error_norm ** (-1/5) (scipy rk.py:157,166) from the SQUARED norm e2 = error_norm^2.
 // Outside [1e-30, 1e30] the caller's clamps (MIN_FACTOR 0.2, MAX_FACTOR 10) decide anyway, so the
 // argument is clamped first; NaN stays NaN (a NaN error norm rejects the step and shrinks h by
@@ -251,6 +274,61 @@ struct LorenzLanes {
         }
         return sumsq(e);
     }
+
+    // FUSED numerics: the same attempt arranged for the tail of the dependent chain.  Everything of the error
+    // estimate that does not need k7 = f(y_new) -- the partial sum of the first six stages, the scale, its
+    // reciprocal (MUFU seed + ONE Newton round: 2^-46) times h -- is formed while the last right-hand side is
+    // in flight, so that ONE FMA per variable follows k7; the squares are summed as two chains.
+    // Returns sum over the chain's variables of (error/scale)^2  (= n * error_norm^2).
+    __device__ __forceinline__ double attempt_fused(const LorenzTheta &th, const double (&y)[NV], const double (&k1)[NV],
+                                                    double h, double rtol, double atol,
+                                                    double (&ynew)[NV], double (&k7)[NV]) const {
+        double k2[NV], k3[NV], k4[NV], k5[NV], k6[NV], ys[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) ys[i] = fma(DP[A21] * k1[i], h, y[i]);
+        rhs(th, ys, k2);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) ys[i] = fma(fma(DP[A32], k2[i], DP[A31] * k1[i]), h, y[i]);
+        rhs(th, ys, k3);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) ys[i] = fma(fma(DP[A43], k3[i], fma(DP[A42], k2[i], DP[A41] * k1[i])), h, y[i]);
+        rhs(th, ys, k4);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            ys[i] = fma(fma(DP[A54], k4[i], fma(DP[A53], k3[i], fma(DP[A52], k2[i], DP[A51] * k1[i]))), h, y[i]);
+        rhs(th, ys, k5);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            ys[i] = fma(fma(DP[A65], k5[i],
+                            fma(DP[A64], k4[i], fma(DP[A63], k3[i], fma(DP[A62], k2[i], DP[A61] * k1[i])))),
+                        h, y[i]);
+        rhs(th, ys, k6);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            ynew[i] = fma(h, fma(DP[B6], k6[i], fma(DP[B5], k5[i], fma(DP[B4], k4[i], fma(DP[B3], k3[i], DP[B1] * k1[i])))),
+                          y[i]);
+        rhs(th, ynew, k7);
+        double S[NV], Q[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const double part = fma(DP[E6], k6[i], fma(DP[E5], k5[i], fma(DP[E4], k4[i], fma(DP[E3], k3[i], DP[E1] * k1[i]))));
+            const double scale = fma(absmax_bits(y[i], ynew[i]), rtol, atol);
+            double r;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(scale));
+            r = fma(r, fma(-scale, r, 1.0), r);
+            const double hr = h * r;
+            S[i] = part * hr;
+            Q[i] = DP[E7] * hr;
+        }
+        double sa = 0.0, sb = 0.0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const double e = fma(k7[i], Q[i], S[i]);
+            if (i & 1) sb = fma(e, e, sb);
+            else sa = fma(e, e, sa);
+        }
+        return group_sum(sa + sb);
+    }
 };
 
 // Per-chain integrator state for the lock-step solve.
@@ -311,9 +389,15 @@ struct LorenzSolve {
         done = !active || !(P.T > 0.0);
         step_rejected = false;
         new_step = true;
+        if (NUM == LNUM_FUSED) attempts_fused(L, P, th);
+        else attempts_exact(L, P, th);
+    }
+
+    // ---- RungeKutta._step_impl (rk.py:118-175), one attempt per iteration, scipy's order of operations
+    __device__ __forceinline__ void attempts_exact(const LorenzLanes<J, KT, NUM> &L, const LorenzDev &P, const LorenzTheta &th) {
+        const double inv_n = 1.0 / (double)P.nvar;
         int guard = 0;
         while (__any_sync(FULL, !done)) {
-            // ---- RungeKutta._step_impl (rk.py:118-175), one attempt per iteration
             const double t_next = __longlong_as_double(__double_as_longlong(t) + 1);  // nextafter(t, +inf), t >= 0
             const double min_step = 10.0 * fabs(t_next - t);
             if (new_step) {
@@ -327,31 +411,17 @@ struct LorenzSolve {
             h = t_new - t;
             const double h_abs_used = fabs(h);
             double ynew[NV], fnew[NV];
-            // error_norm^2; the controller below is branch-free (chains of a warp accept and reject
-            // in the same attempt more often than not) and never takes the square root:
+            // error_norm^2; the controller never takes the square root:
             // error_norm < 1 <=> e2 < 1, error_norm^(-1/5) = e2^(-1/10)
             const double e2 = L.attempt(th, y, f, h, P.rtol, P.atol, ynew, fnew) * inv_n;
             const bool live = !done && !fail;
             const bool acc = live && (e2 < 1.0);
             const bool rej = live && !acc;   // NaN error norms land here too, as in scipy (nan < 1 is False)
-            if (NUM == LNUM_FUSED) {
-                // The clamps of the controller -- factor <= MAX_FACTOR, <= 1 after a rejection, >= MIN_FACTOR
-                // (rk.py:157-171) -- applied to the ARGUMENT of the power instead of its result:
-                // 0.9 x^(-1/10) lies in [0.2, 10] iff x lies in [0.09^10, 4.5^10], and is <= 1 iff x >= 0.9^10
-                // (a rejected attempt has x >= 1 anyway).  One clamp in front of the power, which overlaps
-                // with the error norm, replaces three dependent min/max behind it.
-                const double lo = step_rejected ? 0.3486784401 : 3.486784401e-11;
-                const double x = fmin(fmax(e2, lo), 3405062.8916015625);
-                double fac = RK_SAFETY * pow_m01<1>(x);
-                fac = (e2 != e2) ? RK_MIN_FACTOR : fac;   // NaN error norm: rejected, shrink by MIN_FACTOR
-                if (live) h_abs = h_abs_used * fac;
-            } else {
-                const double raw = rk_raw_factor<2>(e2);
-                double f_acc = (e2 == 0.0) ? RK_MAX_FACTOR : fmin(RK_MAX_FACTOR, raw);
-                if (step_rejected) f_acc = fmin(1.0, f_acc);
-                const double f_rej = fmax(RK_MIN_FACTOR, raw);
-                if (live) h_abs = h_abs_used * (acc ? f_acc : f_rej);
-            }
+            const double raw = rk_raw_factor<2>(e2);
+            double f_acc = (e2 == 0.0) ? RK_MAX_FACTOR : fmin(RK_MAX_FACTOR, raw);
+            if (step_rejected) f_acc = fmin(1.0, f_acc);
+            const double f_rej = fmax(RK_MIN_FACTOR, raw);
+            if (live) h_abs = h_abs_used * (acc ? f_acc : f_rej);
             if (acc) {
                 t = t_new;
 #pragma unroll
@@ -371,6 +441,76 @@ struct LorenzSolve {
             }
             ++guard;
             if (fail || guard >= P.max_attempts) done = true;
+        }
+    }
+
+    // ---- the same controller arranged for the dependent chain that links one attempt to the next
+    // (error norm -> step factor -> h -> first stage).  A lone warp on a sub-partition cannot hide it, so:
+    //  * the accept bookkeeping is branch-free selects (no divergent block of register moves between the
+    //    factor and the next attempt: ptxas schedules them into the shadow of the power);
+    //  * the clamps of the controller (factor <= 10, <= 1 after a rejection, >= 0.2; rk.py:157-171) are
+    //    predicates on the squared error norm evaluated beside the power -- 0.9 x^(-1/10) >= c  <=>
+    //    x <= (0.9/c)^10 -- and select the exact clamp values afterwards;
+    //  * the power is rk_factor_fused (no F2F conversions, one 5-level Newton round);
+    //  * the 1/n of the RMS norm is folded into the thresholds (sum of squares ss = n e2).
+    __device__ __forceinline__ void attempts_fused(const LorenzLanes<J, KT, NUM> &L, const LorenzDev &P, const LorenzTheta &th) {
+        const double n = (double)P.nvar;
+        const double inv_n = 1.0 / n;
+        const double ss_one = n;                              // error_norm < 1
+        const double ss_cap10 = n * 3.486784401e-11;          // raw factor >= 10  <=> e2 <= 0.09^10
+        const double ss_cap1 = n * 0.3486784401;              // raw factor >= 1   <=> e2 <= 0.9^10
+        const double ss_floor = n * 3405062.8916015625;       // raw factor <= 0.2 <=> e2 >= 4.5^10
+        const float log2n_10 = 0.1f * log2f((float)P.nvar);
+        int guard = 0;
+        // min_step = 10 |nextafter(t) - t| (rk.py:122) depends on t alone: carried across the back edge and
+        // recomputed as soon as the accept select has produced t, off the chain factor -> h -> first stage
+        double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);      // t >= 0: no fabs
+        while (__any_sync(FULL, !done)) {
+            if (new_step) {
+                if (h_abs < min_step) h_abs = min_step;
+                step_rejected = false;
+            }
+            const bool fail = h_abs < min_step;
+            double t_new = t + h_abs;
+            const bool clip = t_new - P.T > 0.0;
+            t_new = clip ? P.T : t_new;
+            const bool last = !(t_new < P.T);                  // this attempt ends at t_bound (t_new <= T always)
+            const double h = t_new - t;                        // >= 0
+            double ynew[NV], fnew[NV];
+            const double ss = L.attempt_fused(th, y, f, h, P.rtol, P.atol, ynew, fnew);
+            const bool live = !done && !fail;
+            const bool acc = live && (ss < ss_one);
+            const bool rej = live && !acc;
+            // step factor: raw power beside its clamp predicates (NaN: no predicate holds except the last)
+            const double raw = rk_factor_fused(ss, inv_n, log2n_10);
+            const bool at_cap = ss <= (step_rejected ? ss_cap1 : ss_cap10);   // incl. ss == 0 (rk.py:157-160)
+            const bool at_floor = !(ss < ss_floor);                            // incl. NaN (max(0.2, nan) = 0.2)
+            double fac = at_cap ? (step_rejected ? 1.0 : RK_MAX_FACTOR) : raw;
+            fac = at_floor ? RK_MIN_FACTOR : fac;
+            h_abs = live ? h * fac : h_abs;
+            // accept bookkeeping as selects
+            t = acc ? t_new : t;
+            min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                y[i] = acc ? ynew[i] : y[i];
+                f[i] = acc ? fnew[i] : f[i];
+            }
+            {
+                const double X = acc ? ynew[0] : 0.0, Y0 = (J > 0 && acc) ? ynew[1] : 0.0;
+                msum[0] += X;
+                msum[1] += Y0;
+                msum[2] = fma(X, X, msum[2]);
+                msum[3] = fma(X, Y0, msum[3]);
+                msum[4] = fma(Y0, Y0, msum[4]);
+            }
+            n_t += acc ? 1 : 0;
+            n_acc += acc ? 1 : 0;
+            n_rej += rej ? 1 : 0;
+            new_step = acc || (new_step && !rej);
+            step_rejected = rej || step_rejected;             // cleared at the top of the next new step
+            ++guard;
+            done = done || fail || guard >= P.max_attempts || (acc && last);
         }
     }
 };

@@ -268,6 +268,9 @@ __global__ void __launch_bounds__(256, 1) lorenz_chain_queue_kernel(const __grid
     double *Gs = smem + (size_t)slot * 2 * IPMCMC_MAX_OBS, *r2 = Gs + IPMCMC_MAX_OBS;
     const Group Gp{L.base, P.K, L.k, FULL};
     const long long n_units = (n_chains + groups - 1) / groups;
+    // the launch spreads ceil(n_units / n_CTA) warps per CTA over ALL SMs (engine.cu); the surplus warps of
+    // the last rows leave at once instead of spinning on an empty queue beside a working warp
+    if ((long long)warp * gridDim.x + blockIdx.x >= n_units) return;
     SchedView Q(C.sched, n_units);
     const unsigned long long cap = (unsigned long long)Q.cap;
     const long long items_per_unit = (n_steps + chunk - 1) / chunk;
@@ -354,7 +357,9 @@ __global__ void __launch_bounds__(32) lorenz_attempt_kernel(int K, long long n, 
         }
         th.finish(J);
         L.rhs(th, y, f);
-        const double err = sqrt(L.attempt(th, y, f, h, rtol, atol, yn, fn)) * inv_sqrt_n;
+        const double ss = (NUM == LNUM_FUSED) ? L.attempt_fused(th, y, f, h, rtol, atol, yn, fn)
+                                              : L.attempt(th, y, f, h, rtol, atol, yn, fn);
+        const double err = sqrt(ss) * inv_sqrt_n;
         if (active) {
             double *o = out + c * (2 * nvar + 1);
             lorenz_store_state<J, KT, NUM>(L, o, yn);

@@ -64,7 +64,7 @@ class BurgersFVM(ForwardModel):
         if numerics not in ("exact", "fused"):
             raise ValueError("numerics must be 'exact' or 'fused'")
         self.numerics = numerics
-        self.max_fv_steps = int(max_fv_steps)
+        self.max_fv_steps = int(max_fv_steps)       # 0: the library default, see effective_max_fv_steps
         a, b = self.domain
         dx0 = (b - a) / self.N
         self.x, self.dx = np.linspace(start=a - .5 * dx0, stop=b + .5 * dx0, num=self.N + 2, retstep=True)
@@ -77,6 +77,12 @@ class BurgersFVM(ForwardModel):
         # KL / spectral extension (north star): w0(x) = Riemann(x) + sum_k a_k sin(k pi (x-a)/(b-a)),
         # k = 1..kl_modes, sampled at the N+2 cell centres like the reference samples its IC (rusanov.py:32)
         self.kl_basis = self.sine_basis(self.x, self.domain, self.kl_modes)
+
+    @property
+    def effective_max_fv_steps(self):
+        """Cap on FV time steps per solve (include/ipmcmc.h: max_fv_steps; default 8 N + 256).  A capped
+        solve reports Phi = NaN, i.e. the proposal is rejected and counted in `nonfinite`."""
+        return self.max_fv_steps if self.max_fv_steps > 0 else 8 * self.N + 256
 
     @staticmethod
     def sine_basis(x, domain, m):

@@ -113,7 +113,7 @@ def accept_probability(kind, phi_u, phi_v, u=None, v=None, L=None):
 
 
 def run_chain(potential, u0, normals, uniforms, proposer=PCN, accepter=PCN, step=0.25,
-              prior_cov=None, constraint=None, varstep=False, recompute_phi_u=False):
+              prior_cov=None, constraint=None, varstep=False, recompute_phi_u=False, uniforms_by_step=False):
     """Replay MCMCSampler._step (sampler.py:35-41) len(uniforms)-or-len(normals) times with
     injected noise.  `step` is a scalar (Const* proposers) or an array indexed by step
     (VarStep*, already evaluated at i = 1, 2, ...).
@@ -150,7 +150,9 @@ def run_chain(potential, u0, normals, uniforms, proposer=PCN, accepter=PCN, step
                 phi_u = potential(u)
             phi_v = potential(v)
             a = accept_probability(accepter, phi_u, phi_v, u, v, L)
-            U = uniforms[iu]
+            # the reference draws U only when the constraint holds (accepter.py:52-55): a tape is consumed in
+            # order; the engine's counter-based RNG indexes U by the step number instead (uniforms_by_step)
+            U = uniforms[i] if uniforms_by_step else uniforms[iu]
             iu += 1
             acc = bool(a > U)                # accepter.py:61-62 (NaN -> False)
             out["phi_v"][i] = phi_v

@@ -102,16 +102,19 @@ def test_forward_random_parameters_vs_oracle(G, N):
 def test_fused_on_boundary_ghost_inputs_with_the_cap_lifted(G, N):
     """FUSED numerics on the inputs where the reference's interior-only CFL (rusanov.py:102-109) lets a
     ghost cell sampled from the initial condition (rusanov.py:32) overshoot in the FIRST time step:
-    u = [0.3, -0.2, -0.49] has an all-positive initial condition (ghost 2.8, interior 0.05) and a
-    sign-changing state after step 1 (min u ~ -4e3 at 64 cells).  The select-free positive loop may only be
+    a jump between the left ghost centre and the first cell centre (u = [0.3, -0.2, -0.49] at 64 cells) gives an
+    all-positive initial condition (ghost 2.8, interior 0.05) and a sign-changing state after step 1 (min u ~ -4e3).  The select-free positive loop may only be
     entered on the state AFTER the peeled first step (burgers.cuh: state_positive); with the safety cap
     lifted the FUSED solve must follow the reference through the blow-up: same FV step count, G and Phi
     within the north-star tolerance."""
     rng = np.random.default_rng(100 + N)
-    u = np.concatenate([[[0.3, -0.2, -0.49], [0.3, -0.2, 1.49], [0.3, 0.2, -0.49], [-0.2, -0.3, -0.495]],
+    P = B.BurgersProblem(N)
+    dx = 2.0 / N
+    left_gap = (-1 - 0.25 * dx) - P.prior_mean[2]     # jump between the left ghost centre and the first cell centre
+    right_gap = (1 + 0.25 * dx) - P.prior_mean[2]     # ... between the last cell centre and the right ghost centre
+    u = np.concatenate([[[0.3, -0.2, left_gap], [0.3, -0.2, right_gap], [0.3, 0.2, left_gap], [-0.2, -0.3, left_gap]],
                         np.column_stack([0.25 * rng.standard_normal(8), 0.25 * rng.standard_normal(8),
                                          rng.choice([-0.5, 1.5], 8) + 0.02 * rng.standard_normal(8)])])
-    P = B.BurgersProblem(N)
     fe, pe, _, y = G.burgers_setup(N, "exact", max_fv_steps=10 ** 7)
     ff, pf, _, _ = G.burgers_setup(N, "fused", y=y, max_fv_steps=10 ** 7)
     opot = O.Potential(P, y, G.NOISE_COV)

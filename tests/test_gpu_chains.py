@@ -299,6 +299,69 @@ def test_grid_refinement_study_driver(G):
         assert 0.01 < out[N]["acceptance"] < 0.99
 
 
+def test_device_histogram_matches_numpy(G):
+    """ipmcmc_histogram_accumulate == np.histogramdd (right-open bins, last edge inclusive, outside dropped),
+    accumulated over several calls, with values exactly on edges and a padded row stride."""
+    from ip_mcmc_b200 import studies
+    rng = np.random.default_rng(3)
+    iv = np.array([[-0.5, 0.5], [0.0, 2.0], [-1.0, 0.25]])
+    x = rng.standard_normal((20000, 3)) * [0.3, 0.8, 0.5] + [0.0, 1.0, -0.4]
+    edges = [np.linspace(lo, hi, 21) for lo, hi in iv]
+    x[:21, 0] = edges[0]                     # on every edge of dimension 0 (incl. both ends)
+    x[21:42, 1] = edges[1]
+    x[50] = [0.5, 2.0, 0.25]                 # the upper corner belongs to the last bin
+    shift = np.array([0.1, -0.2, 0.05])
+    h = studies.DeviceHistogram(iv, bins=20, shift=shift)
+    xs = x - shift
+    padded = np.concatenate([xs, np.full((len(xs), 2), 99.0)], axis=1)       # stride 5: extra columns ignored
+    h.add(G.cuda(padded[:7000]))
+    h.add(G.cuda(xs[7000:]))
+    ref, _ = np.histogramdd(xs + shift, bins=20, range=iv)
+    assert np.array_equal(h.counts.cpu().numpy(), ref.astype(np.int64))
+    np.testing.assert_allclose(h.normalised(), ref / ref.sum(), rtol=1e-15)
+
+
+def test_chain_length_study_streams_the_same_histograms(G):
+    """chain_length_study (burgers_wasserstein_chain.py:164-268 on the device): the histograms accumulated launch
+    by launch equal np.histogramdd of the same chains recorded in full and split as the script does; and the
+    chains themselves equal the CPU oracle run with the engine's own Philox noise (VarStep RW + box constraint)."""
+    import ip_mcmc_b200 as M
+    from ip_mcmc_b200 import studies
+    from oracle import philox_np as P
+    N, L, si, B_ = 32, 1200, 5, 3
+    r = studies.chain_length_study(chain_length=L, n_chains=B_, N=N, sample_interval=si, steps_per_launch=170, seed=7)
+    # the same chains recorded in full through the public sampler (same seed, same object graph)
+    pm = np.array([1.5, 0.25, -0.5])
+    f, pot, prior, _ = G.burgers_setup(N)
+    sched = studies.PWLinear(0.05, 0.001, 250)
+    box = M.BoxConstraint([-np.inf, -np.inf, -1.0], [np.inf, np.inf, 1.0], shift=[0.0, 0.0, pm[2]])
+    counted = M.CountedAccepter(M.StandardRWAccepter(pot, prior))
+    s = M.MCMCSampler(M.VarStepStandardRWProposer(sched, prior), M.ConstrainAccepter(counted, box), np.random.default_rng(7))
+    full = s.run(np.zeros(3), L, 0, 1, n_chains=B_)                     # [B, L, 3]
+    thinned = full[:, ::si] + pm
+    chains, rest = [], thinned
+    for _ in range(4):                                                  # burgers_wasserstein_chain.py:261-266
+        l = rest.shape[1] // 2
+        chains.append(rest[:, l + 1:])
+        rest = rest[:, :l]
+    iv = np.stack([np.min([c.reshape(-1, 3).min(0) for c in chains], axis=0),
+                   np.max([c.reshape(-1, 3).max(0) for c in chains], axis=0)], axis=1)
+    np.testing.assert_array_equal(r["intervals"], iv)
+    for k, c in enumerate(chains):
+        ref, _ = np.histogramdd(c.reshape(-1, 3), bins=20, range=iv)
+        assert np.array_equal(r["counts"][k], ref.astype(np.int64)), k
+        assert r["lengths"][k] == c.shape[1]
+    assert r["acceptance"] == pytest.approx(counted.ratio())            # counter inside the constraint
+    # ... and chain 1 against the CPU oracle with the engine's noise
+    z, U = P.chain_noise(s.last_run["seed"], 1, 0, L, 3)
+    Pb = B.BurgersProblem(N)
+    opot = O.Potential(Pb, Pb.G_params(G.TRUTH), G.NOISE_COV)
+    steps = np.array([sched(i) for i in range(1, L + 1)])
+    ref = O.run_chain(opot, np.zeros(3), 0.25 * z, U, O.RW, O.RW, steps, prior_cov=G.PRIOR_COV, varstep=True,
+                      constraint=lambda v: -1.0 < v[2] + pm[2] < 1.0, uniforms_by_step=True)
+    np.testing.assert_allclose(full[1], ref["u"], rtol=1e-12, atol=1e-14)
+
+
 def test_run_into_preallocated_host_buffer(G):
     """`out=`: samples land in a caller-owned (pinned torch or NumPy) host buffer, identical to the
     returned-array path; wrong sizes are refused."""

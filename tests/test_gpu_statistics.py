@@ -68,15 +68,15 @@ def test_burgers_bench_config_statistics_vs_cpu_chains(G):
     chains vs 32 CPU chains x 2500 steps, the first 500 discarded."""
     import ip_mcmc_b200 as M
     N, beta, n_steps, burn = 256, 0.25, 2500, 500
-    f, pot, prior, y = G.burgers_setup(N, "fused")
+    y = B.BurgersProblem(N).G_params(G.TRUTH)          # the reference's noise-free data G(u*), both sides
+    f, pot, prior, _ = G.burgers_setup(N, "fused", y=y)
     start = G.TRUTH - G.PRIOR_MEAN
     s = M.MCMCSampler(M.ConstSteppCNProposer(beta, prior), M.CountedAccepter(M.pCNAccepter(pot)), np.random.default_rng(2))
     dev_states = s.run(start, n_steps, 0, 1, n_chains=1024)
     acc_dev = np.any(np.diff(np.concatenate([np.broadcast_to(start, (1024, 1, 3)), dev_states], axis=1), axis=1) != 0, axis=2)
     assert acc_dev.sum() == s.last_run["counters"]["accepts"]
     assert s.last_run["counters"]["nonfinite"] == 0
-    # CPU: the C restatement with the device's own data vector (y == oracle G(u*), asserted)
-    assert np.array_equal(y, B.BurgersProblem(N).G_params(G.TRUTH))
+    np.testing.assert_allclose(f.at_parameters(G.TRUTH), y, rtol=1e-10)      # FUSED G(u*) vs the reference's
     Pc = CO.BurgersC(N, y=y, noise_cov=G.NOISE_COV)
     rng = np.random.default_rng(77)
     n_cpu = 32

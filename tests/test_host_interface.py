@@ -254,6 +254,19 @@ def test_tau0_matches_reference_fixture():
     assert M.stats.uncorrelated_sample_spacing(g["case5_x"]) == 3
 
 
+def test_chain_segments_match_the_reference_split():
+    """studies.chain_segments == the halving loop of burgers_wasserstein_chain.py:261-266."""
+    from ip_mcmc_b200 import studies
+    for n in (5000, 4999, 37, 16):
+        samples, want = np.arange(n), []
+        for _ in range(4):
+            l = int(len(samples) / 2)
+            want.append(samples[l + 1:])
+            samples = samples[:l]
+        got = [np.arange(a, b) for a, b in studies.chain_segments(n)]
+        assert all(np.array_equal(g, w) for g, w in zip(got, want))
+
+
 def test_studies_histogram_cache_and_schedule(tmp_path):
     from ip_mcmc_b200 import studies
     rng = np.random.default_rng(0)
