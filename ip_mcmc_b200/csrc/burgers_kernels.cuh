@@ -122,14 +122,17 @@ struct ChainRegs {
 
 // ONE Metropolis step of chain c (local id; cg global id) at launch-local step s: proposal -> (box
 // constraint) -> solve -> Phi(v) -> accept/reject -> counters, logs, moments, trace.
+// `phi_of(ui, n_fv)` evaluates Phi for the parameter vector whose component i sits on lane i: the one-warp
+// solver (burgers_phi) or the multi-warp team solver (burgers_team_phi), whose warps all run this same step
+// with the same Philox draws; `writer` (warp 0 of a team; always true for one warp per chain) owns the
+// global-memory outputs.
 #ifndef IPMCMC_STEP_INLINE
 #define IPMCMC_STEP_INLINE __forceinline__
 #endif
-template <int CPL, int NUMERICS, bool PADDED>
-__device__ IPMCMC_STEP_INLINE void burgers_metropolis_step(const BurgersDev &B, const SamplerDev &S, const ChainBufDev &C,
-                                                        const Group &Gp, long long c, long long cg, long long s,
-                                                        long long n_steps, double *state, double *Gs, double *r2,
-                                                        ChainRegs &R) {
+template <class PhiOf>
+__device__ IPMCMC_STEP_INLINE void metropolis_step(const SamplerDev &S, const ChainBufDev &C, const Group &Gp, long long c,
+                                                   long long cg, long long s, long long n_steps, ChainRegs &R,
+                                                   const PhiOf &phi_of, bool writer) {
     const int lane = Gp.lane, d = S.d;
     const long long gstep = S.first_step + s;
     double ca, cb;
@@ -139,7 +142,7 @@ __device__ IPMCMC_STEP_INLINE void burgers_metropolis_step(const BurgersDev &B, 
     const double vi = ca * R.ui + cb * w;
     PROF_T(q1);
     PROF_ADD(2, q0, q1);
-    if (C.vlog && lane < d) C.vlog[(c * n_steps + s) * d + lane] = vi;
+    if (writer && C.vlog && lane < d) C.vlog[(c * n_steps + s) * d + lane] = vi;
     bool accepted = false;
     double phi_v = nan(""), a = nan("");
     int n_fv = 0;
@@ -147,11 +150,11 @@ __device__ IPMCMC_STEP_INLINE void burgers_metropolis_step(const BurgersDev &B, 
     if (ok) {
         if (S.recompute_phi_u) {  // the reference's 2 solves per step (accepter.py:121-122)
             int nf0;
-            R.phi_u = burgers_phi<CPL, NUMERICS, PADDED>(B, R.ui, state, Gs, r2, lane, nf0);
+            R.phi_u = phi_of(R.ui, nf0);
             R.cnt[CNT_WORK_A] += nf0;
             R.cnt[CNT_WORK_B] += 1;
         }
-        phi_v = burgers_phi<CPL, NUMERICS, PADDED>(B, vi, state, Gs, r2, lane, n_fv);
+        phi_v = phi_of(vi, n_fv);
         PROF_T(q2);
         R.cnt[CNT_WORK_A] += n_fv;
         R.cnt[CNT_WORK_B] += 1;
@@ -173,7 +176,7 @@ __device__ IPMCMC_STEP_INLINE void burgers_metropolis_step(const BurgersDev &B, 
     }
     R.cnt[CNT_CALLS] += 1;
     R.cnt[CNT_ACCEPTS] += accepted ? 1 : 0;
-    if (C.steplog && lane == 0) {
+    if (writer && C.steplog && lane == 0) {
         double *L = C.steplog + (c * n_steps + s) * 4;
         L[0] = phi_v;
         L[1] = a;
@@ -184,8 +187,19 @@ __device__ IPMCMC_STEP_INLINE void burgers_metropolis_step(const BurgersDev &B, 
     if (records_step(S, gstep)) {
         R.mom.add(R.ui);
         const long long n_rec = recorded_before(S, gstep) - recorded_before(S, S.first_step);
-        if (C.trace && n_rec < C.n_record && lane < d) C.trace[(c * C.n_record + n_rec) * d + lane] = R.ui;
+        if (writer && C.trace && n_rec < C.n_record && lane < d) C.trace[(c * C.n_record + n_rec) * d + lane] = R.ui;
     }
+}
+
+template <int CPL, int NUMERICS, bool PADDED>
+__device__ IPMCMC_STEP_INLINE void burgers_metropolis_step(const BurgersDev &B, const SamplerDev &S, const ChainBufDev &C,
+                                                        const Group &Gp, long long c, long long cg, long long s,
+                                                        long long n_steps, double *state, double *Gs, double *r2,
+                                                        ChainRegs &R) {
+    const int lane = Gp.lane;
+    metropolis_step(S, C, Gp, c, cg, s, n_steps, R,
+                    [&](double ui, int &n_fv) { return burgers_phi<CPL, NUMERICS, PADDED>(B, ui, state, Gs, r2, lane, n_fv); },
+                    true);
 }
 
 // W warps per CTA, one chain per warp.  Warps never synchronise with each other; the CTA shape
@@ -393,88 +407,39 @@ __global__ void __launch_bounds__(32 * TM) burgers_team_chain_kernel(const __gri
     const bool writer = tw == 0;  // all warps run the same Metropolis logic; warp 0 owns the global writes
     const Group Gp{0, 32, lane, FULL};
     const int d = S.d;
+    const auto phi_of = [&](double ui, int &n_fv) {
+        return burgers_team_phi<CPL, NUMERICS, TM>(B, X, ui, state, Gs, r2, tw, lane, n_fv);
+    };
     for (long long c = blockIdx.x; c < n_chains; c += gridDim.x) {
         const long long cg = S.chain_offset + c;
-        double ui = (lane < d) ? C.u[c * d + lane] : 0.0;
-        double phi_u = C.phi[c];
-        long long cnt[CNT_N];
+        ChainRegs R;
+        R.ui = (lane < d) ? C.u[c * d + lane] : 0.0;
+        R.phi_u = C.phi[c];
 #pragma unroll
-        for (int k = 0; k < CNT_N; ++k) cnt[k] = 0;
-        int n_fv;
+        for (int k = 0; k < CNT_N; ++k) R.cnt[k] = 0;
         __syncthreads();  // everyone has read the chain state before warp 0 may overwrite it at the end
-        if (isnan(phi_u)) {
-            phi_u = burgers_team_phi<CPL, NUMERICS, TM>(B, X, ui, state, Gs, r2, tw, lane, n_fv);
-            cnt[CNT_WORK_A] += n_fv;
-            cnt[CNT_WORK_B] += 1;
+        if (isnan(R.phi_u)) {
+            int n_fv;
+            R.phi_u = phi_of(R.ui, n_fv);
+            R.cnt[CNT_WORK_A] += n_fv;
+            R.cnt[CNT_WORK_B] += 1;
         }
-        double reg_u = (S.accepter == IPMCMC_ACCEPT_RW) ? prior_regulariser(S, Gp, ui) : 0.0;
-        Welford mom{C.mom_count[c], (lane < d) ? C.mom_mean[c * d + lane] : 0.0,
-                    (lane < d) ? C.mom_m2[c * d + lane] : 0.0};
-        long long n_rec = 0;
-        for (long long s = 0; s < n_steps; ++s) {
-            const long long gstep = S.first_step + s;
-            double ca, cb;
-            step_coefs(S, gstep, ca, cb);
-            const double w = proposal_noise(S, C, Gp, c, cg, s, n_steps, gstep);
-            const double vi = ca * ui + cb * w;
-            if (writer && C.vlog && lane < d) C.vlog[(c * n_steps + s) * d + lane] = vi;
-            bool accepted = false;
-            double phi_v = nan(""), a = nan("");
-            n_fv = 0;
-            const bool ok = !S.has_constraint || constraint_ok(S, Gp, vi);
-            if (ok) {
-                if (S.recompute_phi_u) {
-                    int nf0;
-                    phi_u = burgers_team_phi<CPL, NUMERICS, TM>(B, X, ui, state, Gs, r2, tw, lane, nf0);
-                    cnt[CNT_WORK_A] += nf0;
-                    cnt[CNT_WORK_B] += 1;
-                }
-                phi_v = burgers_team_phi<CPL, NUMERICS, TM>(B, X, vi, state, Gs, r2, tw, lane, n_fv);
-                cnt[CNT_WORK_A] += n_fv;
-                cnt[CNT_WORK_B] += 1;
-                double reg_v = 0.0;
-                if (S.accepter == IPMCMC_ACCEPT_RW) reg_v = prior_regulariser(S, Gp, vi);
-                a = exp((phi_u + reg_u) - (phi_v + reg_v));
-                const double U = C.inject_u ? C.inject_u[c * n_steps + s]
-                                            : draw_uniform(S.seed, (uint64_t)cg, (uint64_t)gstep);
-                accepted = a > U;
-                if (!isfinite(phi_v)) cnt[CNT_NONFINITE] += 1;
-                if (accepted) {
-                    ui = vi;
-                    phi_u = phi_v;
-                    reg_u = reg_v;
-                }
-            } else {
-                cnt[CNT_CONSTRAINT] += 1;
-            }
-            cnt[CNT_CALLS] += 1;
-            cnt[CNT_ACCEPTS] += accepted ? 1 : 0;
-            if (writer && C.steplog && lane == 0) {
-                double *L = C.steplog + (c * n_steps + s) * 4;
-                L[0] = phi_v;
-                L[1] = a;
-                L[2] = accepted ? 1.0 : 0.0;
-                L[3] = (double)n_fv;
-            }
-            if (records_step(S, gstep)) {
-                mom.add(ui);
-                if (writer && C.trace && n_rec < C.n_record && lane < d)
-                    C.trace[(c * C.n_record + n_rec) * d + lane] = ui;
-                ++n_rec;
-            }
-        }
+        R.reg_u = (S.accepter == IPMCMC_ACCEPT_RW) ? prior_regulariser(S, Gp, R.ui) : 0.0;
+        R.mom = Welford{C.mom_count[c], (lane < d) ? C.mom_mean[c * d + lane] : 0.0,
+                        (lane < d) ? C.mom_m2[c * d + lane] : 0.0};
+        for (long long s = 0; s < n_steps; ++s) metropolis_step(S, C, Gp, c, cg, s, n_steps, R, phi_of, writer);
         __syncthreads();
         if (writer) {
             if (lane < d) {
-                C.u[c * d + lane] = ui;
-                C.mom_mean[c * d + lane] = mom.mean;
-                C.mom_m2[c * d + lane] = mom.m2;
+                C.u[c * d + lane] = R.ui;
+                C.mom_mean[c * d + lane] = R.mom.mean;
+                C.mom_m2[c * d + lane] = R.mom.m2;
             }
             if (lane == 0) {
-                C.phi[c] = phi_u;
-                C.mom_count[c] = mom.count;
+                C.phi[c] = R.phi_u;
+                C.mom_count[c] = R.mom.count;
 #pragma unroll
-                for (int k = 0; k < CNT_N; ++k) C.counters[c * CNT_N + k] += cnt[k];
+                for (int k = 0; k < CNT_N; ++k) C.counters[c * CNT_N + k] += R.cnt[k];
             }
         }
         __syncthreads();

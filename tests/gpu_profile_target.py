@@ -78,7 +78,7 @@ elif what == "chainflat":
     y = f.at_parameters(TRUTH)
     pot = M.EvolutionPotential(f, y, M.GaussianDistribution(np.zeros(5), 0.05 ** 2 * np.identity(5)))
     S = 20
-    for nch in (592, 1024, 1036, 1184, 2368, 8192):
+    for nch in (592, 1024, 1184, 1776, 2048, 2368, 4736, 8192):
         spec = M.SamplerSpec(3, _lib.PROPOSE_PCN, _lib.ACCEPT_PCN, coef_u=1.0, coef_w=0.0)
         ch = M.ChainBatch(pot.problem(), TRUTH - PM, n_chains=nch)
         w = torch.zeros((nch, S, 3), dtype=torch.float64, device="cuda")
@@ -91,5 +91,5 @@ elif what == "chainflat":
             ts.append(e0.elapsed_time(e1))
             nfv = (ch.counters[:, 2].sum().item() - c0) / nch
         t = min(ts)
-        print("chains %5d W=%d (%.2f warps/SMSP): %.3f ms, %d FV steps/chain -> %.0f cycles per FV step per warp-slot, TFLOP/s %.2f"
-              % (nch, ch.placement.W, nch / 592.0, t, nfv, t * 1e-3 * 1.965e9 / nfv, 29.0 * N * nfv * nch / (t * 1e-3) / 1e12))
+        print("chains %5d (%.2f warps/SMSP): %.3f ms, %d FV steps/chain -> %.0f cycles per FV step per warp-slot, TFLOP/s %.2f"
+              % (nch, nch / 592.0, t, nfv, t * 1e-3 * 1.965e9 / nfv, 29.0 * N * nfv * nch / (t * 1e-3) / 1e12), flush=True)

@@ -51,8 +51,10 @@ def test_bench_kernel_time_step_loop_schedule(tmp_path):
     with open(sass, "w") as f:
         subprocess.run(["cuobjdump", "-sass", "-fun", fun, lib], stdout=f, stderr=subprocess.DEVNULL, check=False)
     loops = _time_step_loops(str(sass), "burgers_chain_queue_kernelILi8ELi1ELb0ELi2E")
-    # two rotated time-step loops (burgers.cuh, time_loop_pipelined), each nested in the loop that repairs a
-    # wrong high-word guess: keep the innermost ones -- the select-free one (positive states) and the general one
+    # four rotated time-step loops per solve (burgers.cuh): the monotone-state ones (time_loop_mono: max|u| from the
+    # two end cells; what a Riemann initial condition runs) for positive and for sign-changing states, and the
+    # general ones (time_loop_pipelined, nested in the loop that repairs a wrong high-word guess) that KL modes
+    # and blow-up solves fall back to.  Pin the hot ones: the leanest loop of each fp64 class.
     inner = {}
     for n_ins, n_f64, stalls in loops:
         key = "pos" if n_f64 < 125 else "gen"
@@ -60,7 +62,8 @@ def test_bench_kernel_time_step_loop_schedule(tmp_path):
             inner[key] = (n_ins, n_f64, stalls)
     assert set(inner) == {"pos", "gen"}, "expected the positive-state and the general time-step loop, found %r" % (loops,)
     pos, gen = inner["pos"], inner["gen"]
+    assert pos[0] <= 160 and gen[0] <= 210, "instructions per 256-cell time step grew: %r" % (loops,)
     assert pos[1] <= 116 and gen[1] <= 134, "fp64 instructions per 256-cell time step grew: %r" % (loops,)
-    assert pos[2] <= 330 and gen[2] <= 400, (
-        "ptxas serialised a time-step loop (static stall sums %d / %d, limits 330 / 400): unrelated edits move "
+    assert pos[2] <= 300 and gen[2] <= 350, (
+        "ptxas serialised a time-step loop (static stall sums %d / %d, limits 300 / 350): unrelated edits move "
         "its register allocation; see tools/sass_loops.py and DESIGN.md section 4.1" % (pos[2], gen[2]))
