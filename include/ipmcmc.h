@@ -47,6 +47,13 @@ enum {
     IPMCMC_NUMERICS_FUSED = 1  /* FMA-contracted update; agrees with EXACT to <= 3.4e-11 relative */
 };
 
+/* ipmcmc_burgers_desc.flags */
+enum {
+    IPMCMC_BURGERS_NO_MONOTONE_SHORTCUT = 1 /* FUSED numerics: always reduce max|u| over all cells for the CFL
+                                               step instead of taking it from the two end cells of a monotone
+                                               state (results are bit-identical; used by the tests to prove it) */
+};
+
 /* proposal / acceptance kinds */
 enum { IPMCMC_PROPOSE_RW = 0, IPMCMC_PROPOSE_PCN = 1 };
 enum { IPMCMC_ACCEPT_RW = 0, IPMCMC_ACCEPT_PCN = 1 };
@@ -102,7 +109,7 @@ typedef struct ipmcmc_burgers_desc {
        w0(x) = PerturbedRiemannIC(x) + sum_k a_k * phi_k(x), the coefficients a_k being parameters
        3..3+m-1 with a diagonal (KL) prior.  kl_basis is phi_k at the N+2 cell centres.          */
     int32_t n_kl_modes;       /* m (0 = the reference's 3-parameter problem)                    */
-    int32_t reserved;
+    int32_t flags;            /* IPMCMC_BURGERS_* bits (0 = default)                            */
     const double *kl_basis;   /* host [m * (N+2)], row-major (mode, cell); NULL when m = 0      */
     ipmcmc_potential_desc potential;
 } ipmcmc_burgers_desc;

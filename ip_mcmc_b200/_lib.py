@@ -13,6 +13,7 @@ MODEL_BURGERS, MODEL_LORENZ = 1, 2
 NUMERICS_EXACT, NUMERICS_FUSED = 0, 1
 PROPOSE_RW, PROPOSE_PCN = 0, 1
 ACCEPT_RW, ACCEPT_PCN = 0, 1
+BURGERS_NO_MONOTONE_SHORTCUT = 1
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -28,7 +29,7 @@ class BurgersDesc(C.Structure):
     _fields_ = [("n_cells", C.c_int32), ("numerics", C.c_int32), ("max_fv_steps", C.c_int32),
                 ("n_params", C.c_int32), ("T", C.c_double), ("dx", C.c_double), ("dx_meas", C.c_double),
                 ("x", c_double_p), ("param_mean", c_double_p), ("win_left", c_int32_p),
-                ("win_right", c_int32_p), ("n_kl_modes", C.c_int32), ("reserved", C.c_int32),
+                ("win_right", c_int32_p), ("n_kl_modes", C.c_int32), ("flags", C.c_int32),
                 ("kl_basis", c_double_p), ("potential", PotentialDesc)]
 
 

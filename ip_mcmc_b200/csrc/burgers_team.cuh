@@ -149,7 +149,7 @@ struct BurgersTeam {
         }
         positive = __syncthreads_and(pos) != 0;
         const bool ni_all = __syncthreads_and(ni) != 0, nd_all = __syncthreads_and(nd) != 0;
-        monotone = allow_mono && (ni_all || nd_all);
+        monotone = IPMCMC_MONO && allow_mono && (ni_all || nd_all);
     }
     // end-of-solve guard of the monotone shortcut (BurgersWarp::mono_end_ok)
     __device__ __forceinline__ bool mono_end_ok(TeamXch &X, int tw, int lane) {
@@ -302,8 +302,9 @@ struct BurgersTeam {
         int n = 0;
         for (int pass = 0; pass < 2; ++pass) {   // second pass only if the guard of the monotone shortcut fails
             init_state(B, pi, tw, lane);
-            if (NUMERICS == NUM_FUSED || B.dx_pow2) n = time_loop<true>(C, X, tw, lane, pass == 0);
-            else n = time_loop<false>(C, X, tw, lane, pass == 0);
+            const bool allow_mono = pass == 0 && !B.no_mono;
+            if (NUMERICS == NUM_FUSED || B.dx_pow2) n = time_loop<true>(C, X, tw, lane, allow_mono);
+            else n = time_loop<false>(C, X, tw, lane, allow_mono);
             if (!(NUMERICS == NUM_FUSED && monotone && !capped) || mono_end_ok(X, tw, lane)) break;
         }
         return n;

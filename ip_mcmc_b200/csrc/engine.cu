@@ -150,6 +150,7 @@ extern "C" int ipmcmc_burgers_create(const ipmcmc_burgers_desc *d, ipmcmc_proble
     int ex;
     b.dx_pow2 = (std::frexp(d->dx, &ex) == 0.5) ? 1 : 0;
     b.dx_meas = d->dx_meas;
+    b.no_mono = (d->flags & IPMCMC_BURGERS_NO_MONOTONE_SHORTCUT) ? 1 : 0;
     for (int i = 0; i < b.d; ++i) b.param_mean[i] = d->param_mean[i];
     int rc = fill_potential(p, d->potential, b.pot);
     if (rc) { ipmcmc_destroy(p); return rc; }

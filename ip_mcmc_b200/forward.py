@@ -47,7 +47,7 @@ class BurgersFVM(ForwardModel):
 
     def __init__(self, domain=(-1, 1), N=200, T=1, prior_means=(1.5, 0.25, -0.5),
                  points=(-0.5, -0.25, 0.25, 0.5, 0.75), interval=0.1, numerics="exact", max_fv_steps=0,
-                 kl_modes=0):
+                 kl_modes=0, monotone_shortcut=True):
         self.domain = (float(domain[0]), float(domain[1]))
         self.N = int(N)
         self.T = float(T)
@@ -65,6 +65,9 @@ class BurgersFVM(ForwardModel):
             raise ValueError("numerics must be 'exact' or 'fused'")
         self.numerics = numerics
         self.max_fv_steps = int(max_fv_steps)       # 0: the library default, see effective_max_fv_steps
+        # FUSED numerics: take max|u| of a monotone state from its two end cells (bit-identical results; the
+        # switch exists so that the tests can prove it)
+        self.monotone_shortcut = bool(monotone_shortcut)
         a, b = self.domain
         dx0 = (b - a) / self.N
         self.x, self.dx = np.linspace(start=a - .5 * dx0, stop=b + .5 * dx0, num=self.N + 2, retstep=True)
@@ -102,6 +105,7 @@ class BurgersFVM(ForwardModel):
         d.max_fv_steps = self.max_fv_steps
         d.n_params = self.n_params
         d.n_kl_modes = self.kl_modes
+        d.flags = 0 if self.monotone_shortcut else _lib.BURGERS_NO_MONOTONE_SHORTCUT
         if self.kl_modes:
             d.kl_basis = _lib.as_double_p(self.kl_basis)
             keep.append(self.kl_basis)
@@ -127,7 +131,8 @@ class BurgersFVM(ForwardModel):
         prior mean) would round differently)."""
         if getattr(self, "_abs_model", None) is None:
             self._abs_model = BurgersFVM(self.domain, self.N, self.T, np.zeros(self.n_params), self.points,
-                                         self.interval, self.numerics, self.max_fv_steps, self.kl_modes)
+                                         self.interval, self.numerics, self.max_fv_steps, self.kl_modes,
+                                         self.monotone_shortcut)
         return self._abs_model(params)
 
 

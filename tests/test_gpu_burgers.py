@@ -130,6 +130,26 @@ def test_fused_on_boundary_ghost_inputs_with_the_cap_lifted(G, N):
     np.testing.assert_allclose(phf, phe, rtol=RTOL)
 
 
+@pytest.mark.parametrize("N", [64, 100, 256, 1024, 2048])
+def test_monotone_cfl_shortcut_is_bit_identical(G, N):
+    """FUSED numerics take max|u| of a state that is monotone in x from its two end cells (burgers.cuh,
+    time_loop_mono; the scheme preserves monotonicity, |u| of a monotone profile peaks at an end).  With the
+    shortcut switched off (IPMCMC_BURGERS_NO_MONOTONE_SHORTCUT) every solve reduces over all cells: G, Phi, the
+    end state and the FV step count must be bit-identical over prior draws incl. rarefactions, sign changes and
+    jumps at / outside both boundaries (where the first step breaks monotonicity and the general loop takes over)."""
+    import ip_mcmc_b200 as M
+    rng = np.random.default_rng(N)
+    n = 2048 if N <= 256 else 256
+    u = 0.25 * rng.standard_normal((n, 3))
+    u[: n // 4, 2] = rng.uniform(-0.55, 1.55, n // 4)
+    u[0] = [0.3, -0.2, (-1 - 0.5 / N) + 0.5]         # jump between the left ghost and the first cell centre: blow-up
+    a = M.BurgersFVM(N=N, numerics="fused").batch(u, want_state=True)
+    b = M.BurgersFVM(N=N, numerics="fused", monotone_shortcut=False).batch(u, want_state=True)
+    for k in ("G", "phi", "state", "work"):
+        assert np.array_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), equal_nan=True), k
+    assert a["work"][:, 0].max().item() == 8 * N + 256          # some blow-up solves hit the cap in both
+
+
 def test_callable_interfaces_match_reference_semantics(G):
     """observation_operator(u) -> ndarray[q]; potential(u) -> float (potential.py:53-54)."""
     g = golden("burgers_forward_N64.npz")
