@@ -28,7 +28,11 @@ extern "C" {
 
 #define IPMCMC_ABI_VERSION 2
 
-#define IPMCMC_MAX_DIM 32   /* parameter dimension d   (3 in every reference script)          */
+#define IPMCMC_MAX_DIM 32   /* parameter dimension d held on the lanes of one warp (3 in every
+                               reference script): every feature, dynamic scheduler, team solver    */
+#define IPMCMC_MAX_DIM_WIDE 256 /* Burgers with a truncated KL prior of up to 253 modes: the parameter
+                               vector lives in shared memory ("wide path"): N <= 1024 cells, diagonal
+                               sampling factor (factor_kind 0/1), diagonal prior_chol, static scheduler */
 #define IPMCMC_MAX_OBS 64   /* observation dimension q (5 Burgers, 5K = 30 Lorenz)            */
 
 enum {

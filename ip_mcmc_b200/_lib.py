@@ -6,7 +6,8 @@ import os
 from . import build as _build
 
 ABI_VERSION = 2
-MAX_DIM = 32
+MAX_DIM = 32          # parameter vector on the lanes of one warp
+MAX_DIM_WIDE = 256    # Burgers KL prior: parameter vector in shared memory (include/ipmcmc.h)
 MAX_OBS = 64
 N_COUNTERS = 6
 MODEL_BURGERS, MODEL_LORENZ = 1, 2

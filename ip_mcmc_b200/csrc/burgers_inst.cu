@@ -19,7 +19,13 @@ namespace ipmcmc {
                                                                        cudaStream_t);                                \
     template cudaError_t burgers_launch_chain_queue<IPMCMC_TU_CPL, NUM, PAD>(const BurgersDev &, const SamplerDev &,    \
                                                                              const ChainBufDev &, long long, long long, \
-                                                                             int, cudaStream_t);
+                                                                             int, cudaStream_t);                     \
+    template cudaError_t burgers_launch_wide_forward<IPMCMC_TU_CPL, NUM, PAD>(const BurgersDev &, long long,            \
+                                                                              const double *, double *, double *,     \
+                                                                              double *, long long *, cudaStream_t);   \
+    template cudaError_t burgers_launch_wide_chain<IPMCMC_TU_CPL, NUM, PAD>(const BurgersDev &, const SamplerDev &,     \
+                                                                            const ChainBufDev &, long long, long long, \
+                                                                            cudaStream_t);
 INST(NUM_EXACT, false)
 INST(NUM_EXACT, true)
 INST(NUM_FUSED, false)

@@ -340,6 +340,199 @@ __global__ void __launch_bounds__(256, MINB) burgers_chain_queue_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
+// wide parameter vectors (IPMCMC_MAX_DIM < d <= IPMCMC_MAX_DIM_WIDE): the truncated KL / spectral prior
+// with up to 253 modes.  One chain per warp as before, but the parameter vector no longer fits the lanes
+// of the warp: u, the proposal v and the absolute parameters live in shared memory (component i is served
+// by lane i % 32), the solver reads its parameters from there (BurgersWarp::integrate over a ParamAt
+// functor), the running moments are updated in place in global memory.  Same Philox draws (slot = component),
+// same accept rule; diagonal sampling factor and diagonal prior factor only (what a KL prior is); static
+// chain -> warp map.  CPU statement: oracle/mcmc_np.run_chain + oracle/burgers_np with kl_basis.
+// ------------------------------------------------------------------------------------------------
+// shared memory per warp: state[N] | G[MAX_OBS] | r2[MAX_OBS] | par[d] | u[d] | v[d]
+__host__ __device__ inline size_t burgers_wide_smem_bytes(int N, int d, int warps = 1) {
+    return (size_t)warps * (N + 2 * IPMCMC_MAX_OBS + 3 * d) * sizeof(double);
+}
+
+// Phi for the parameter perturbation x[0..d) (shared memory); par[] is scratch for mean + x
+template <int CPL, int NUMERICS, bool PADDED>
+__device__ __forceinline__ double burgers_phi_wide(const BurgersDev &B, const double *x, double *par, double *state,
+                                                   double *Gs, double *r2, int lane, int &n_fv) {
+    for (int i = lane; i < B.d; i += 32) par[i] = B.param_mean_wide[i] + x[i];   // utilities.py:41
+    __syncwarp();
+    BurgersWarp<CPL, NUMERICS, PADDED> W;
+    n_fv = W.integrate(B, [par](int i) { return par[i]; }, lane);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+        const int c = lane * CPL + k;
+        if (c < B.N) state[c] = W.u[k];
+    }
+    __syncwarp();
+    burgers_measure(B, state, Gs, lane);
+    const double phi = potential_from_G(B.pot, Gs, r2, lane, 32, FULL);
+    return W.capped ? nan("") : phi;
+}
+
+// sum over the warp in a fixed order (lane tree), the same bits on every lane
+__device__ __forceinline__ double warp_sum_fixed(double v) {
+#pragma unroll
+    for (int off = 1; off < 32; off *= 2) {
+        const double o = __shfl_xor_sync(FULL, v, off);
+        v = (lane_id() & off) ? o + v : v + o;
+    }
+    return v;
+}
+
+// 0.5 * ||L x||^2 for a diagonal L (accepter.py:104-106)
+__device__ __forceinline__ double prior_regulariser_wide(const SamplerDev &S, const double *x, int lane) {
+    double ss = 0.0;
+    for (int i = lane; i < S.d; i += 32) {
+        const double y = S.prior_chol_diag[i] * x[i];
+        ss = ss + y * y;
+    }
+    const double nrm = sqrt(warp_sum_fixed(ss));
+    return 0.5 * (nrm * nrm);
+}
+
+template <int CPL, int NUMERICS, bool PADDED>
+__global__ void __launch_bounds__(128) burgers_wide_forward_kernel(const __grid_constant__ BurgersDev B, long long n,
+                                                                   const double *__restrict__ u, double *__restrict__ G,
+                                                                   double *__restrict__ phi, double *__restrict__ state_out,
+                                                                   long long *__restrict__ work) {
+    extern __shared__ double smem_all[];
+    const int warp = threadIdx.x >> 5, wpc = blockDim.x >> 5, d = B.d;
+    double *smem = smem_all + (size_t)warp * (B.N + 2 * IPMCMC_MAX_OBS + 3 * d);
+    double *state = smem, *Gs = smem + B.N, *r2 = Gs + IPMCMC_MAX_OBS, *par = r2 + IPMCMC_MAX_OBS, *x = par + d;
+    const int lane = lane_id();
+    for (long long c = (long long)blockIdx.x * wpc + warp; c < n; c += (long long)gridDim.x * wpc) {
+        for (int i = lane; i < d; i += 32) x[i] = u[c * d + i];
+        __syncwarp();
+        int n_fv;
+        const double ph = burgers_phi_wide<CPL, NUMERICS, PADDED>(B, x, par, state, Gs, r2, lane, n_fv);
+        if (G)
+            for (int i = lane; i < B.pot.q; i += 32) G[c * B.pot.q + i] = Gs[i];
+        if (state_out)
+            for (int i = lane; i < B.N; i += 32) state_out[c * B.N + i] = state[i];
+        if (lane == 0) {
+            if (phi) phi[c] = ph;
+            if (work) {
+                work[2 * c] = n_fv;
+                work[2 * c + 1] = 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int CPL, int NUMERICS, bool PADDED>
+__global__ void __launch_bounds__(128) burgers_wide_chain_kernel(const __grid_constant__ BurgersDev B,
+                                                                 const __grid_constant__ SamplerDev S,
+                                                                 const __grid_constant__ ChainBufDev C, long long n_chains,
+                                                                 long long n_steps) {
+    extern __shared__ double smem_all[];
+    const int warp = threadIdx.x >> 5, wpc = blockDim.x >> 5, d = S.d;
+    double *smem = smem_all + (size_t)warp * (B.N + 2 * IPMCMC_MAX_OBS + 3 * d);
+    double *state = smem, *Gs = smem + B.N, *r2 = Gs + IPMCMC_MAX_OBS, *par = r2 + IPMCMC_MAX_OBS, *us = par + d, *vs = us + d;
+    const int lane = lane_id();
+    for (long long c = (long long)blockIdx.x * wpc + warp; c < n_chains; c += (long long)gridDim.x * wpc) {
+        const long long cg = S.chain_offset + c;
+        for (int i = lane; i < d; i += 32) us[i] = C.u[c * d + i];
+        __syncwarp();
+        double phi_u = C.phi[c];
+        long long cnt[CNT_N];
+#pragma unroll
+        for (int k = 0; k < CNT_N; ++k) cnt[k] = 0;
+        if (isnan(phi_u)) {  // first launch: Phi(u_0) not known yet
+            int n_fv;
+            phi_u = burgers_phi_wide<CPL, NUMERICS, PADDED>(B, us, par, state, Gs, r2, lane, n_fv);
+            cnt[CNT_WORK_A] += n_fv;
+            cnt[CNT_WORK_B] += 1;
+        }
+        double reg_u = (S.accepter == IPMCMC_ACCEPT_RW) ? prior_regulariser_wide(S, us, lane) : 0.0;
+        double count = C.mom_count[c];
+        for (long long s = 0; s < n_steps; ++s) {
+            const long long gstep = S.first_step + s;
+            double ca, cb;
+            step_coefs(S, gstep, ca, cb);
+            // proposal (proposer.py:29-30, 81-82): v = ca*u + cb*w, w_i = factor_i * z_i, z_i = Philox slot i
+            bool inside = true;
+            for (int i = lane; i < d; i += 32) {
+                double w;
+                if (C.inject_w) {
+                    w = C.inject_w[(c * n_steps + s) * d + i];
+                } else {
+                    const double z = draw_normal(S.seed, (uint64_t)cg, (uint64_t)gstep, (uint32_t)i);
+                    w = S.factor_kind == 1 ? S.factor[i] * z : z;
+                }
+                const double vi = ca * us[i] + cb * w;
+                vs[i] = vi;
+                if (C.vlog) C.vlog[(c * n_steps + s) * d + i] = vi;
+                if (S.has_constraint) {
+                    const double sh = vi + S.box_wide[2 * d + i];
+                    inside = inside && (sh > S.box_wide[i]) && (sh < S.box_wide[d + i]);
+                }
+            }
+            __syncwarp();
+            const bool ok = !S.has_constraint || __all_sync(FULL, inside);
+            bool accepted = false;
+            double phi_v = nan(""), a = nan("");
+            int n_fv = 0;
+            if (ok) {
+                if (S.recompute_phi_u) {  // the reference's 2 solves per step (accepter.py:121-122)
+                    int nf0;
+                    phi_u = burgers_phi_wide<CPL, NUMERICS, PADDED>(B, us, par, state, Gs, r2, lane, nf0);
+                    cnt[CNT_WORK_A] += nf0;
+                    cnt[CNT_WORK_B] += 1;
+                }
+                phi_v = burgers_phi_wide<CPL, NUMERICS, PADDED>(B, vs, par, state, Gs, r2, lane, n_fv);
+                cnt[CNT_WORK_A] += n_fv;
+                cnt[CNT_WORK_B] += 1;
+                const double reg_v = (S.accepter == IPMCMC_ACCEPT_RW) ? prior_regulariser_wide(S, vs, lane) : 0.0;
+                a = exp((phi_u + reg_u) - (phi_v + reg_v));
+                const double U = C.inject_u ? C.inject_u[c * n_steps + s] : draw_uniform(S.seed, (uint64_t)cg, (uint64_t)gstep);
+                accepted = a > U;  // strict, un-clipped; NaN compares false (accepter.py:61-62)
+                if (!isfinite(phi_v)) cnt[CNT_NONFINITE] += 1;
+                if (accepted) {
+                    for (int i = lane; i < d; i += 32) us[i] = vs[i];
+                    phi_u = phi_v;
+                    reg_u = reg_v;
+                }
+                __syncwarp();
+            } else {
+                cnt[CNT_CONSTRAINT] += 1;
+            }
+            cnt[CNT_CALLS] += 1;
+            cnt[CNT_ACCEPTS] += accepted ? 1 : 0;
+            if (C.steplog && lane == 0) {
+                double *L = C.steplog + (c * n_steps + s) * 4;
+                L[0] = phi_v;
+                L[1] = a;
+                L[2] = accepted ? 1.0 : 0.0;
+                L[3] = (double)n_fv;
+            }
+            if (records_step(S, gstep)) {   // Welford in place (sampler.py:23-28)
+                count += 1.0;
+                const long long n_rec = recorded_before(S, gstep) - recorded_before(S, S.first_step);
+                for (int i = lane; i < d; i += 32) {
+                    const double x = us[i], m0 = C.mom_mean[c * d + i];
+                    const double delta = x - m0, m1 = m0 + delta / count;
+                    C.mom_mean[c * d + i] = m1;
+                    C.mom_m2[c * d + i] += delta * (x - m1);
+                    if (C.trace && n_rec < C.n_record) C.trace[(c * C.n_record + n_rec) * d + i] = x;
+                }
+            }
+        }
+        for (int i = lane; i < d; i += 32) C.u[c * d + i] = us[i];
+        if (lane == 0) {
+            C.phi[c] = phi_u;
+            C.mom_count[c] = count;
+#pragma unroll
+            for (int k = 0; k < CNT_N; ++k) C.counters[c * CNT_N + k] += cnt[k];
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // team kernels: one CTA of TM warps per chain (N = TM*32*CPL cells > 1024)
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t burgers_team_smem_bytes(int N) {

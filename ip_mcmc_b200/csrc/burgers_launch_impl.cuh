@@ -89,6 +89,32 @@ cudaError_t burgers_launch_chain_queue(const BurgersDev &b, const SamplerDev &S,
     return cudaSuccess;
 }
 
+// wide parameter vectors: 4 warps per CTA unless the shared memory of 4 does not fit
+template <int CPL, int NUM, bool PAD>
+cudaError_t burgers_launch_wide_forward(const BurgersDev &b, long long n, const double *u, double *G, double *phi,
+                                       double *state, long long *work, cudaStream_t st) {
+    int wpc = n >= 4 * 148 ? 4 : 1;
+    while (wpc > 1 && burgers_wide_smem_bytes(b.N, b.d, wpc) > 200 * 1024) wpc /= 2;
+    const size_t smem = burgers_wide_smem_bytes(b.N, b.d, wpc);
+    auto kern = burgers_wide_forward_kernel<CPL, NUM, PAD>;
+    if (smem > 48 * 1024) IPMCMC_CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid_for((n + wpc - 1) / wpc), 32 * wpc, smem, st>>>(b, n, u, G, phi, state, work);
+    IPMCMC_CU(cudaGetLastError());
+    return cudaSuccess;
+}
+template <int CPL, int NUM, bool PAD>
+cudaError_t burgers_launch_wide_chain(const BurgersDev &b, const SamplerDev &S, const ChainBufDev &C, long long n_chains,
+                                     long long n_steps, cudaStream_t st) {
+    int wpc = n_chains >= 4 * 148 ? 4 : 1;
+    while (wpc > 1 && burgers_wide_smem_bytes(b.N, S.d, wpc) > 200 * 1024) wpc /= 2;
+    const size_t smem = burgers_wide_smem_bytes(b.N, S.d, wpc);
+    auto kern = burgers_wide_chain_kernel<CPL, NUM, PAD>;
+    if (smem > 48 * 1024) IPMCMC_CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid_for((n_chains + wpc - 1) / wpc), 32 * wpc, smem, st>>>(b, S, C, n_chains, n_steps);
+    IPMCMC_CU(cudaGetLastError());
+    return cudaSuccess;
+}
+
 template <int NUM, int TM>
 cudaError_t burgers_launch_team_forward(const BurgersDev &b, long long n, const double *u, double *G, double *phi,
                                        double *state, long long *work, cudaStream_t st) {

@@ -129,7 +129,9 @@ extern "C" int ipmcmc_burgers_create(const ipmcmc_burgers_desc *d, ipmcmc_proble
     if (d->n_cells < 2) return fail(IPMCMC_EINVAL, "n_cells=%d < 2", d->n_cells);
     if (!pick_cpl(d->n_cells) && d->n_cells != 2048 && d->n_cells != 4096)
         return fail(IPMCMC_EUNSUPPORTED, "n_cells=%d: grids above 1024 cells must be 2048 or 4096 (2 or 4 warps per chain)", d->n_cells);
-    if (d->n_kl_modes < 0 || d->n_kl_modes > IPMCMC_MAX_DIM - 3) return fail(IPMCMC_EUNSUPPORTED, "n_kl_modes=%d outside [0,%d]", d->n_kl_modes, IPMCMC_MAX_DIM - 3);
+    if (d->n_kl_modes < 0 || d->n_kl_modes > IPMCMC_MAX_DIM_WIDE - 3) return fail(IPMCMC_EUNSUPPORTED, "n_kl_modes=%d outside [0,%d]", d->n_kl_modes, IPMCMC_MAX_DIM_WIDE - 3);
+    if (d->n_params > IPMCMC_MAX_DIM && d->n_cells > 1024)
+        return fail(IPMCMC_EUNSUPPORTED, "more than %d parameters (wide path) need n_cells <= 1024", IPMCMC_MAX_DIM);
     if (d->n_params != 3 + d->n_kl_modes) return fail(IPMCMC_EINVAL, "n_params=%d, expected 3 + n_kl_modes = %d", d->n_params, 3 + d->n_kl_modes);
     if (d->n_kl_modes > 0 && !d->kl_basis) return fail(IPMCMC_EINVAL, "kl_basis is NULL");
     if (d->numerics != IPMCMC_NUMERICS_EXACT && d->numerics != IPMCMC_NUMERICS_FUSED) return fail(IPMCMC_EINVAL, "bad numerics");
@@ -151,8 +153,15 @@ extern "C" int ipmcmc_burgers_create(const ipmcmc_burgers_desc *d, ipmcmc_proble
     b.dx_pow2 = (std::frexp(d->dx, &ex) == 0.5) ? 1 : 0;
     b.dx_meas = d->dx_meas;
     b.no_mono = (d->flags & IPMCMC_BURGERS_NO_MONOTONE_SHORTCUT) ? 1 : 0;
-    for (int i = 0; i < b.d; ++i) b.param_mean[i] = d->param_mean[i];
-    int rc = fill_potential(p, d->potential, b.pot);
+    for (int i = 0; i < b.d && i < IPMCMC_MAX_DIM; ++i) b.param_mean[i] = d->param_mean[i];
+    int rc = 0;
+    if (b.d > IPMCMC_MAX_DIM) {   // wide path: the means as a device table
+        void *pm;
+        rc = upload(p, d->param_mean, sizeof(double) * b.d, &pm);
+        if (rc) { ipmcmc_destroy(p); return rc; }
+        b.param_mean_wide = (const double *)pm;
+    }
+    rc = fill_potential(p, d->potential, b.pot);
     if (rc) { ipmcmc_destroy(p); return rc; }
     for (int i = 0; i < b.pot.q; ++i) {
         const int l = d->win_left[i], r = d->win_right[i];
@@ -292,6 +301,8 @@ extern "C" int ipmcmc_forward(ipmcmc_problem *p, int64_t n, const double *u_dev,
     if (p->model == IPMCMC_MODEL_BURGERS) {
         if (p->b.N > 1024)
             BURGERS_TEAM_DISPATCH(burgers_launch_team_forward, p->b, n, u_dev, G_dev, phi_dev, state_dev, (long long *)work_dev, st);
+        if (p->b.d > IPMCMC_MAX_DIM)
+            BURGERS_DISPATCH(burgers_launch_wide_forward, p->b, n, u_dev, G_dev, phi_dev, state_dev, (long long *)work_dev, st);
         BURGERS_DISPATCH(burgers_launch_forward, p->b, n, u_dev, G_dev, phi_dev, state_dev, (long long *)work_dev, st);
     }
     if (!state_dev) return fail(IPMCMC_EINVAL, "Lorenz forward needs state_dev (carried initial condition)");
@@ -309,8 +320,10 @@ extern "C" int ipmcmc_forward(ipmcmc_problem *p, int64_t n, const double *u_dev,
 // ------------------------------------------------------------------------------------------------
 static int make_sampler(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, SamplerDev &S, int64_t n_chains) {
     const int d = s->dim;
-    if (d < 1 || d > IPMCMC_MAX_DIM) return fail(IPMCMC_EINVAL, "dim=%d outside [1,%d]", d, IPMCMC_MAX_DIM);
+    if (d < 1 || d > IPMCMC_MAX_DIM_WIDE) return fail(IPMCMC_EINVAL, "dim=%d outside [1,%d]", d, IPMCMC_MAX_DIM_WIDE);
     if (p->model == IPMCMC_MODEL_BURGERS && d != p->b.d) return fail(IPMCMC_EINVAL, "dim=%d but the forward model takes %d parameters", d, p->b.d);
+    const bool wide = d > IPMCMC_MAX_DIM;
+    if (wide && s->factor_kind == 2) return fail(IPMCMC_EUNSUPPORTED, "dim=%d > %d: the wide path samples with a diagonal factor only", d, IPMCMC_MAX_DIM);
     if (p->model == IPMCMC_MODEL_LORENZ && d != 3) return fail(IPMCMC_EINVAL, "dim=%d but the Lorenz operator takes (F,h,b)", d);
     if (s->proposer != IPMCMC_PROPOSE_RW && s->proposer != IPMCMC_PROPOSE_PCN) return fail(IPMCMC_EINVAL, "bad proposer");
     if (s->accepter != IPMCMC_ACCEPT_RW && s->accepter != IPMCMC_ACCEPT_PCN) return fail(IPMCMC_EINVAL, "bad accepter");
@@ -337,11 +350,33 @@ static int make_sampler(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, Sampler
         int rc = cached_table(p, s->factor, s->factor_kind == 1 ? (size_t)d : (size_t)d * d, &S.factor);
         if (rc) return rc;
     }
-    if (s->accepter == IPMCMC_ACCEPT_RW) {
+    if (s->accepter == IPMCMC_ACCEPT_RW && !wide) {
         int rc = cached_table(p, s->prior_chol, (size_t)d * d, &S.prior_chol);
         if (rc) return rc;
     }
-    if (s->has_constraint) {
+    if (s->accepter == IPMCMC_ACCEPT_RW && wide) {   // diagonal prior factor only
+        std::vector<double> diag(d);
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j < d; ++j) {
+                if (i == j) diag[i] = s->prior_chol[(size_t)i * d + j];
+                else if (s->prior_chol[(size_t)i * d + j] != 0.0)
+                    return fail(IPMCMC_EUNSUPPORTED, "dim=%d > %d: the wide path needs a diagonal prior_chol", d, IPMCMC_MAX_DIM);
+            }
+        int rc = cached_table(p, diag.data(), (size_t)d, &S.prior_chol_diag);
+        if (rc) return rc;
+    }
+    if (s->has_constraint && wide) {
+        if (!s->box_lo || !s->box_hi) return fail(IPMCMC_EINVAL, "constraint box is NULL");
+        std::vector<double> box(3 * (size_t)d);
+        for (int i = 0; i < d; ++i) {
+            box[i] = s->box_lo[i];
+            box[d + i] = s->box_hi[i];
+            box[2 * d + i] = s->box_shift ? s->box_shift[i] : 0.0;
+        }
+        int rc = cached_table(p, box.data(), box.size(), &S.box_wide);
+        if (rc) return rc;
+    }
+    if (s->has_constraint && !wide) {
         if (!s->box_lo || !s->box_hi) return fail(IPMCMC_EINVAL, "constraint box is NULL");
         for (int i = 0; i < d; ++i) {
             S.box_lo[i] = s->box_lo[i];
@@ -390,6 +425,7 @@ extern "C" int ipmcmc_run(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, const
         if (wpc > 8) return fail(IPMCMC_EINVAL, "warps_per_cta=%d > 8", wpc);
         if (b->slot_chain_dev && b->n_slots < 1) return fail(IPMCMC_EINVAL, "slot_chain_dev without n_slots");
         if (p->b.N > 1024) BURGERS_TEAM_DISPATCH(burgers_launch_team_chain, p->b, S, C, n_chains, n_steps, st);
+        if (S.d > IPMCMC_MAX_DIM) BURGERS_DISPATCH(burgers_launch_wide_chain, p->b, S, C, n_chains, n_steps, st);
         if (b->sched_dev) {
             if (b->sched_len < sched_len(n_chains))
                 return fail(IPMCMC_EINVAL, "sched_len=%lld < 3*n_chains+2", (long long)b->sched_len);
@@ -555,7 +591,7 @@ static int pool_launch(long long n_chains, int d, const double *cnt, const doubl
 extern "C" int ipmcmc_pool_moments(int64_t n_chains, int32_t dim, const double *mom_count_dev,
                                    const double *mom_mean_dev, const double *mom_m2_dev, const int64_t *counters_dev,
                                    double *pooled_dev, void *scratch_dev, int64_t scratch_bytes, void *stream) {
-    if (dim < 1 || dim > IPMCMC_MAX_DIM) return fail(IPMCMC_EINVAL, "dim=%d", dim);
+    if (dim < 1 || dim > IPMCMC_MAX_DIM_WIDE) return fail(IPMCMC_EINVAL, "dim=%d", dim);
     if (n_chains < 1) return fail(IPMCMC_EINVAL, "n_chains=%lld", (long long)n_chains);
     if (!mom_count_dev || !mom_mean_dev || !mom_m2_dev || !counters_dev || !pooled_dev) return fail(IPMCMC_EINVAL, "NULL argument");
     const int64_t need = ipmcmc_pool_scratch_bytes(n_chains, dim);
@@ -622,7 +658,9 @@ __global__ void fill_kernel(double *p, long long n, double v) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 
-static bool uses_queue(const ipmcmc_problem *p) { return p->model == IPMCMC_MODEL_LORENZ || p->b.N <= 1024; }
+static bool uses_queue(const ipmcmc_problem *p) {
+    return p->model == IPMCMC_MODEL_LORENZ || (p->b.N <= 1024 && p->b.d <= IPMCMC_MAX_DIM);
+}
 
 extern "C" int ipmcmc_sample_host(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, int64_t n_chains, int64_t n_steps,
                                   const ipmcmc_host_io *io, void *stream) {
@@ -630,7 +668,7 @@ extern "C" int ipmcmc_sample_host(ipmcmc_problem *p, const ipmcmc_sampler_desc *
     if (n_chains <= 0 || n_steps < 0) return fail(IPMCMC_EINVAL, "n_chains=%lld n_steps=%lld", (long long)n_chains, (long long)n_steps);
     const int d = s->dim;
     const int d_model = p->model == IPMCMC_MODEL_LORENZ ? 3 : p->b.d;
-    if (d < 1 || d > IPMCMC_MAX_DIM || d != d_model) return fail(IPMCMC_EINVAL, "dim=%d but the forward model takes %d parameters", d, d_model);
+    if (d < 1 || d > IPMCMC_MAX_DIM_WIDE || d != d_model) return fail(IPMCMC_EINVAL, "dim=%d but the forward model takes %d parameters", d, d_model);
     if (io->n_record < 0) return fail(IPMCMC_EINVAL, "n_record=%lld", (long long)io->n_record);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t B = (size_t)n_chains;

@@ -24,6 +24,9 @@ struct SamplerDev {
     const double *factor;      // device [d] or [d*d]
     const double *prior_chol;  // device [d*d]
     double box_lo[IPMCMC_MAX_DIM], box_hi[IPMCMC_MAX_DIM], box_shift[IPMCMC_MAX_DIM];
+    // wide path (IPMCMC_MAX_DIM < d <= IPMCMC_MAX_DIM_WIDE): device tables instead of the arrays above
+    const double *box_wide;         // [3*d] = lo | hi | shift, or nullptr
+    const double *prior_chol_diag;  // [d] diagonal of the prior Cholesky factor (ACCEPT_RW), or nullptr
     unsigned long long seed;
     long long chain_offset, first_step, record_start, record_interval;
 };

@@ -238,7 +238,7 @@ class ChainBatch:
                 raise ValueError("scheduler must be 'dynamic' or 'static'")
         if problem.kind == _lib.MODEL_BURGERS:
             n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-            if scheduler == "dynamic" and problem.model.N <= 1024:
+            if scheduler == "dynamic" and problem.model.N <= 1024 and d <= _lib.MAX_DIM:
                 self.sched = torch.empty((3 * self.n + 2,), dtype=torch.int64, device=dev)
             elif scheduler not in ("dynamic", "static"):
                 raise ValueError("scheduler must be 'dynamic' or 'static'")

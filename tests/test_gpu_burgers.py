@@ -285,3 +285,73 @@ def test_kl_spectral_extension(G, N, m):
     # the high modes are weakly informed: their posterior spread stays within the prior's
     post_sd = out[:, 100:, 3:].reshape(-1, m).std(0)
     assert np.all(post_sd < 1.5 * np.sqrt(lam[3:]))
+
+
+@pytest.mark.parametrize("N,m,numerics", [(128, 61, "exact"), (100, 125, "exact"), (256, 61, "fused")])
+def test_kl_prior_beyond_one_warp_of_parameters(G, N, m, numerics):
+    """The wide path (32 < d <= 256: parameter vector, proposal and absolute parameters in shared memory;
+    include/ipmcmc.h IPMCMC_MAX_DIM_WIDE): a truncated KL prior with m = 61 / 125 modes.  Forward solves against
+    the oracle (whose KL initial condition is pinned to the reference's solver by burgers_kl_*.npz), a pCN and a
+    box-constrained RW chain replayed with injected noise (every decision), and free-running chains against the
+    oracle driven by the engine's own Philox noise; on-device moments against the recorded trace."""
+    import ip_mcmc_b200 as M
+    from ip_mcmc_b200 import _lib
+    from oracle import philox_np as Ph
+    d = 3 + m
+    f = M.BurgersFVM(N=N, kl_modes=m, numerics=numerics)
+    P = B.BurgersProblem(N, kl_basis=f.kl_basis)
+    rng = np.random.default_rng(m)
+    lam = np.concatenate([np.full(3, 0.25 ** 2), M.BurgersFVM.kl_prior_variances(m, scale=0.05)])
+    truth = np.concatenate([G.TRUTH, 0.3 * np.sqrt(lam[3:]) * rng.standard_normal(m)])
+    y = P.G_params(truth)
+    tol = dict(rtol=0, atol=0) if numerics == "exact" else dict(rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(f.at_parameters(truth), y, **tol)
+    noise = M.GaussianDistribution(np.zeros(5), G.NOISE_COV)
+    pot = M.EvolutionPotential(f, y, noise)
+    opot = O.Potential(P, y, G.NOISE_COV)
+    # forward
+    u = rng.standard_normal((9, d)) * np.sqrt(lam) * 0.5
+    r = pot.problem().forward(u, want_state=True)
+    for i in range(9):
+        np.testing.assert_allclose(r["G"][i].cpu().numpy(), P.G(u[i]), **tol)
+        assert r["work"][i, 0].item() == P.last_n_fv
+        np.testing.assert_allclose(r["phi"][i].item(), opot(u[i]), rtol=0 if numerics == "exact" else RTOL)
+    # injected-noise replays: pCN, and RW with a box on the shock position
+    prior = M.GaussianDistribution(f.prior_means, np.diag(lam))
+    n, beta, delta = 20, 0.2, 0.02
+    w = rng.standard_normal((n, d)) * np.sqrt(lam)
+    U = rng.random(n)
+    ref = O.run_chain(opot, np.zeros(d), w, U, O.PCN, O.PCN, beta)
+    spec = M.SamplerSpec(d, _lib.PROPOSE_PCN, _lib.ACCEPT_PCN, coef_u=np.sqrt(1 - beta ** 2), coef_w=beta)
+    states, slog, vlog, ch = G.run_injected(pot, spec, np.zeros(d), w, U, n_copies=5)
+    assert ch.sched is None                                     # static map on the wide path
+    for c in (0, 4):
+        assert np.array_equal(states[c], ref["u"]) and np.array_equal(vlog[c], ref["v"])
+        np.testing.assert_allclose(slog[c, :, 0], ref["phi_v"], rtol=0 if numerics == "exact" else RTOL)
+    assert ref["accepts"] > 0 and ch.counters[:, 1].tolist() == [ref["accepts"]] * 5
+    lo, hi = -0.62, -0.38
+    box = M.BoxConstraint(np.r_[-np.inf, -np.inf, lo, np.full(m, -np.inf)], np.r_[np.inf, np.inf, hi, np.full(m, np.inf)],
+                          shift=np.r_[0, 0, -0.5, np.zeros(m)])
+    refc = O.run_chain(opot, np.zeros(d), w, U, O.RW, O.RW, delta, prior_cov=np.diag(lam),
+                       constraint=lambda v: lo < v[2] - 0.5 < hi, uniforms_by_step=True)
+    specc = M.SamplerSpec(d, _lib.PROPOSE_RW, _lib.ACCEPT_RW, coef_u=1.0, coef_w=np.sqrt(2 * delta), prior_chol=prior.L,
+                          constraint=box)
+    states, slog, vlog, ch = G.run_injected(pot, specc, np.zeros(d), w, U, n_copies=2)
+    assert np.array_equal(states[1], refc["u"])
+    valid = ~np.isnan(refc["a"])
+    assert ch.counters[1, 5].item() == (~valid).sum() and (~valid).sum() > 0
+    np.testing.assert_allclose(slog[1, valid, 1], refc["a"][valid], rtol=1e-12 if numerics == "exact" else 1e-6, atol=1e-300)
+    # free-running through the public API, against the oracle with the engine's Philox noise
+    s = M.MCMCSampler(M.ConstSteppCNProposer(beta, prior), M.CountedAccepter(M.pCNAccepter(pot)), np.random.default_rng(3))
+    out = s.run(np.zeros(d), 60, 0, 1, n_chains=37)
+    assert out.shape == (37, 60, d)
+    for c in (0, 36):
+        z, Uc = Ph.chain_noise(s.last_run["seed"], c, 0, 60, d)
+        refp = O.run_chain(opot, np.zeros(d), z * np.sqrt(lam), Uc, O.PCN, O.PCN, beta)
+        np.testing.assert_allclose(out[c], refp["u"], rtol=1e-12 if numerics == "exact" else 1e-9, atol=1e-14)
+    flat = out.reshape(-1, d)
+    np.testing.assert_allclose(s.last_run["pooled_mean"], flat.mean(0), rtol=1e-9, atol=1e-14)
+    np.testing.assert_allclose(s.last_run["pooled_var"], flat.var(0, ddof=1), rtol=1e-8)
+    # the host entry point takes the same path
+    h = M.MCMCSampler(M.ConstSteppCNProposer(beta, prior), M.CountedAccepter(M.pCNAccepter(pot)), np.random.default_rng(3))
+    assert np.array_equal(h.run_host(np.zeros(d), 60, 0, 1, n_chains=37), out)

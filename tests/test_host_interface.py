@@ -59,6 +59,10 @@ def test_argument_validation_without_gpu():
         _lib.check(rc)
     d.n_cells = 5000
     assert lib.ipmcmc_burgers_create(ctypes.byref(d), ctypes.byref(h)) == -3
+    d.n_cells, d.n_kl_modes, d.n_params = 256, 254, 257           # beyond IPMCMC_MAX_DIM_WIDE
+    assert lib.ipmcmc_burgers_create(ctypes.byref(d), ctypes.byref(h)) == -3 and b"n_kl_modes" in lib.ipmcmc_last_error()
+    d.n_cells, d.n_kl_modes, d.n_params = 2048, 40, 43             # the wide path has no team solver
+    assert lib.ipmcmc_burgers_create(ctypes.byref(d), ctypes.byref(h)) == -3 and b"wide path" in lib.ipmcmc_last_error()
     ld = _lib.LorenzDesc()
     ld.K, ld.J = 40, 4
     assert lib.ipmcmc_lorenz_create(ctypes.byref(ld), ctypes.byref(h)) == -3
