@@ -330,7 +330,7 @@ def main():
         c0 = chains.counters.sum(0).cpu().numpy()
         # NVML init happens here, before the barrier.  Every rank samples its own GPU (rank 0 at 10 Hz for
         # the contract's `clocks` key, the others at 4 Hz: enough to tell a slow GPU from a slow host)
-        sampler_clk = ClockSampler(local, interval=0.1 if rank == 0 else 0.25)
+        sampler_clk = ClockSampler(local, interval=0.02 if rank == 0 else 0.25)
         if world > 1:
             parallel.allreduce_pooled(chains.pooled(), 3)   # warm NCCL with the message of the final reduce
             dist.barrier()
