@@ -362,6 +362,23 @@ def test_chain_length_study_streams_the_same_histograms(G):
     np.testing.assert_allclose(full[1], ref["u"], rtol=1e-12, atol=1e-14)
 
 
+def test_chain_length_study_at_the_reference_scale(G):
+    """The script's own size (burgers_wasserstein_chain.py:165: 100 000 steps, N = 128, thinning 20) for 64 chains:
+    4 x 20^3 counters instead of 64 x 100 000 x 3 samples; every thinned sample of every sub-chain lands in a bin
+    (the intervals are the sub-chains' own extrema), longer sub-chains concentrate around the truth's bin."""
+    from ip_mcmc_b200 import studies
+    r = studies.chain_length_study(chain_length=100000, n_chains=64, steps_per_launch=10000)
+    assert r["lengths"] == [2499, 1249, 624, 312]                       # 5000 thinned samples, halved four times
+    for k, n in enumerate(r["lengths"]):
+        assert int(r["counts"][k].sum()) == 64 * n
+        np.testing.assert_allclose(r["histograms"][k].sum(), 1.0, rtol=1e-12)
+    assert 0.05 < r["acceptance"] < 0.95 and r["ground_truth_bin"] is not None
+    # marginal of delta_1 (axis 0): the posterior mass sits within a few bins of the truth's bin
+    gt = r["ground_truth_bin"][0]
+    marg = r["histograms"][0].sum(axis=(1, 2))
+    assert marg[max(gt - 4, 0):gt + 5].sum() > 0.5
+
+
 def test_run_into_preallocated_host_buffer(G):
     """`out=`: samples land in a caller-owned (pinned torch or NumPy) host buffer, identical to the
     returned-array path; wrong sizes are refused."""
