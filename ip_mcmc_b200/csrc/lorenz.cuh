@@ -13,6 +13,11 @@
 #pragma once
 #include "common.cuh"
 
+// developer switch for A/B measurements (tools/build_lorenz_variants.py): the two-level group sum of the FUSED path
+#ifndef IPMCMC_LORENZ_GSUM2
+#define IPMCMC_LORENZ_GSUM2 1
+#endif
+
 namespace ipmcmc {
 
 struct LorenzDev {
@@ -49,13 +54,19 @@ __device__ __forceinline__ double rcp_newton(double x) {
 struct LorenzTheta {
     double F, h, c, b;
     double hc, hJ;  // h*c (lorenz.py:42) and h/J (lorenz.py:98), hoisted out of the RHS
-    double nbc, chJ, nhcJ;  // FUSED numerics: -b*c, c*h/J, -h*c/J
+    // FUSED numerics integrate the SCALED fast variables Z = s*Y, s = -b*c (rhs_fused): s, 1/s,
+    // s*c*h/J (forcing of Z by X) and -(h*c/J)/s (coupling of X to sum Z)
+    double s, inv_s, sA, mS;
     __device__ __forceinline__ void finish(int J) {
         hc = h * c;
         hJ = h / (double)J;
-        nbc = -(b * c);
-        chJ = c * hJ;
-        nhcJ = -(hc / (double)J);
+        // |s| is kept away from zero: below 1e-30 the quadratic term s*Y*dY is far under the rounding of c*Y
+        // whatever the scale, so the clamped scale integrates the same equations to rounding (NaN stays NaN)
+        const double s0 = -(b * c);
+        s = (fabs(s0) < 1e-30) ? copysign(1e-30, s0) : s0;
+        inv_s = 1.0 / s;
+        sA = s * (c * hJ);
+        mS = -(hc / (double)J) * inv_s;
     }
 };
 
@@ -75,13 +86,15 @@ __device__ __forceinline__ double pow_m01(double x) {
     return y;
 }
 
-// FUSED controller: 0.9 * x^(-1/10) for a positive normal x inside the fp32 range, ~5e-13 relative.
+// FUSED controller: h * 0.9 * x^(-1/10) for a positive normal x inside the fp32 range, ~5e-13 relative.
 // Seed on the SFU in fp32 WITHOUT the slow F2F conversions or the denormal fix-ups of __log2f/exp2f
 // (x is re-biased into an fp32 bit pattern with two integer instructions, the result widened the same way;
 // lg2/ex2.approx.ftz), then one Newton round y <- y (1 + (1 - x y^10)/10) arranged in 5 dependent levels
-// (y2 | y4, x*y2 | y8 | 1 - (x y2) y8 | fma) with SAFETY folded in.  Garbage in (0, inf, NaN, out of the
-// fp32 range) gives garbage out: the caller overrides those cases by predicates on x.
-__device__ __forceinline__ double rk_factor_fused(double ss, double inv_n, float log2n_10) {
+// (y2 | y4, x*y2 | y8 | 1 - (x y2) y8 | fma) with SAFETY and the step h folded into the last FMA (h*0.9y and
+// h*0.09y form beside the chain), so that the next step size is ONE instruction behind the residual.
+// Garbage in (0, inf, NaN, out of the fp32 range) gives garbage out: the caller overrides those cases by
+// predicates on x.
+__device__ __forceinline__ double rk_hfactor_fused(double ss, double inv_n, float log2n_10, double h) {
     // seed straight from the bits of ss = n*e2: (ss/n)^(-1/10) = 2^(-0.1 lg2(ss) + 0.1 lg2(n)), the 1/n as one FFMA
     const uint32_t hi = (uint32_t)__double2hiint(ss), lo = (uint32_t)__double2loint(ss);
     const float xf = __uint_as_float(((hi - 0x38000000u) << 3) | (lo >> 29));      // truncated, 2^-23 relative
@@ -91,11 +104,12 @@ __device__ __forceinline__ double rk_factor_fused(double ss, double inv_n, float
     const uint32_t yb = __float_as_uint(yf);
     const double y = __hiloint2double((int)((yb >> 3) + 0x38000000u), (int)(yb << 29));   // exact widening
     const double x = ss * inv_n;                                                   // beside the SFU chain
-    const double y2 = y * y, y09 = y * RK_SAFETY, y009 = y * (0.1 * RK_SAFETY);
+    const double h09 = h * RK_SAFETY, h009 = h * (0.1 * RK_SAFETY);                // beside the SFU chain
+    const double y2 = y * y, hy09 = y * h09, hy009 = y * h009;
     const double y4 = y2 * y2, a = x * y2;
     const double y8 = y4 * y4;
     const double r = fma(-a, y8, 1.0);
-    return fma(y009, r, y09);
+    return fma(hy009, r, hy09);
 }
 
 // SAFETY * error_norm ** (-1/5) (scipy rk.py:157,166) from the SQUARED norm e2 = error_norm^2.
@@ -156,10 +170,47 @@ struct LorenzLanes {
         return __shfl_sync(FULL, s, base);
     }
 
-    // FUSED numerics: the same right-hand side contracted for the fp64 pipe (24 instead of 45
-    // instructions at J = 4):
-    //   dY_j = c*(-Y_j - b*Y_{j+1}*(Y_{j+2} - Y_{j-1}) + (h/J) X) = fma(-bc*Y_{j+1}, Y_{j+2}-Y_{j-1}, fma(-c, Y_j, (ch/J) X))
-    //   dX   = F - X - X_{k-1}*(X_{k-2} - X_{k+1}) - (hc/J) sum_j Y_j
+    // FUSED numerics, even K known at compile time: neighbours add up first (a + b and b + a are the same bits,
+    // so both lanes of a pair hold one value), then every lane gathers the K/2 pair sums and adds them in lane
+    // order: 1 + K/2 shuffles of 64 bits instead of K (K = 6: 8 SHFL.32 instead of 12, and the gather no
+    // longer queues six deep in front of the step-size controller).  Identical bits on every lane of the group.
+    __device__ __forceinline__ double group_sum_fast(double v) const {
+        if (IPMCMC_LORENZ_GSUM2 && KT > 0 && KT % 2 == 0) {
+            constexpr int KH = KT > 0 ? KT / 2 : 1;
+            const double p = v + __shfl_xor_sync(FULL, v, 1);      // base is even: the partner is in the group
+            double g[KH];
+#pragma unroll
+            for (int i = 0; i < KH; ++i) g[i] = __shfl_sync(FULL, p, base + 2 * i);
+#pragma unroll
+            for (int w = 1; w < KH; w *= 2)
+#pragma unroll
+                for (int i = 0; i + w < KH; i += 2 * w) g[i] = g[i] + g[i + w];
+            return g[0];
+        }
+        return group_sum(v);
+    }
+
+    // FUSED numerics integrate Z_j = s*Y_j (s = -b*c, LorenzTheta): state in / out of the scaled variables
+    __device__ __forceinline__ void to_scaled(const LorenzTheta &th, double (&y)[NV]) const {
+        if (NUM == LNUM_FUSED) {
+#pragma unroll
+            for (int j = 1; j < NV; ++j) y[j] = y[j] * th.s;
+        }
+    }
+    __device__ __forceinline__ void from_scaled(const LorenzTheta &th, double (&y)[NV]) const {
+        if (NUM == LNUM_FUSED) {
+#pragma unroll
+            for (int j = 1; j < NV; ++j) y[j] = y[j] * th.inv_s;
+        }
+    }
+
+    // FUSED numerics: the same right-hand side contracted for the fp64 pipe, in the scaled fast variables
+    // Z_j = s*Y_j, s = -b*c, which turn the quadratic coefficient into 1 (20 instead of 45 instructions at J = 4;
+    // 24 with the products s*Y_{j+1} formed per evaluation):
+    //   dY_j = c*(-Y_j - b*Y_{j+1}*(Y_{j+2} - Y_{j-1}) + (h/J) X)
+    //   dZ_j = s*dY_j = Z_{j+1}*(Z_{j+2} - Z_{j-1}) - c*Z_j + (s*c*h/J) X  = fma(Z_{j+1}, Z_{j+2}-Z_{j-1}, fma(-c, Z_j, sA*X))
+    //   dX   = F - X - X_{k-1}*(X_{k-2} - X_{k+1}) - (hc/J) sum_j Y_j,   (hc/J) sum Y = -mS * sum Z
+    // y[0] = X_k, y[1+j] = Z_{k,j}; dy likewise (d/dt of the scaled variables).
     __device__ __forceinline__ void rhs_fused(const LorenzTheta &th, const double (&y)[NV], double (&dy)[NV]) const {
         const double X = y[0];
         const double Xm1 = __shfl_sync(FULL, X, src_m1);
@@ -167,10 +218,8 @@ struct LorenzLanes {
         const double Xp1 = __shfl_sync(FULL, X, src_p1);
         double out = th.F - X;
         if (J > 0) {
-            const double A = th.chJ * X;
-            double g[J], t[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) g[j] = th.nbc * y[1 + j];
+            const double A = th.sA * X;
+            double t[J];
 #pragma unroll
             for (int j = 0; j < J; ++j) t[j] = y[1 + j];
 #pragma unroll
@@ -180,9 +229,9 @@ struct LorenzLanes {
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const double e = y[1 + (j + 2) % J] - y[1 + (j + J - 1) % J];
-                dy[1 + j] = fma(g[(j + 1) % J], e, fma(-th.c, y[1 + j], A));
+                dy[1 + j] = fma(y[1 + (j + 1) % J], e, fma(-th.c, y[1 + j], A));
             }
-            out = fma(th.nhcJ, t[0], out);
+            out = fma(th.mS, t[0], out);
         }
         dy[0] = fma(-Xm1, Xm2 - Xp1, out);
     }
@@ -280,13 +329,20 @@ struct LorenzLanes {
     // reciprocal (MUFU seed + ONE Newton round: 2^-46) times h -- is formed while the last right-hand side is
     // in flight, so that ONE FMA per variable follows k7; the squares are summed as two chains.
     // Returns sum over the chain's variables of (error/scale)^2  (= n * error_norm^2).
-    __device__ __forceinline__ double attempt_fused(const LorenzTheta &th, const double (&y)[NV], const double (&k1)[NV],
-                                                    double h, double rtol, double atol,
-                                                    double (&ynew)[NV], double (&k7)[NV]) const {
-        double k2[NV], k3[NV], k4[NV], k5[NV], k6[NV], ys[NV];
+    // `atol_z` = atol*|s|: the absolute tolerance of the scaled fast variables (error/scale is scale-free).
+    // `ys2` = y + h*a21*k1, the state of the second stage (stage2()): the caller forms it at the END of the previous
+    // attempt (rotated loop, attempts_fused), so that everything between the step-size controller and the first
+    // right-hand side of the next attempt lies in ONE basic block and ptxas schedules the accept selects into the
+    // shadow of the power instead of behind it.
+    __device__ __forceinline__ void stage2(const double (&y)[NV], const double (&k1)[NV], double h, double (&ys2)[NV]) const {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) ys[i] = fma(DP[A21] * k1[i], h, y[i]);
-        rhs(th, ys, k2);
+        for (int i = 0; i < NV; ++i) ys2[i] = fma(DP[A21] * k1[i], h, y[i]);
+    }
+    __device__ __forceinline__ double attempt_fused(const LorenzTheta &th, const double (&y)[NV], const double (&k1)[NV],
+                                                    const double (&ys2)[NV], double h, double rtol, double atol,
+                                                    double atol_z, double (&ynew)[NV], double (&k7)[NV]) const {
+        double k2[NV], k3[NV], k4[NV], k5[NV], k6[NV], ys[NV];
+        rhs(th, ys2, k2);
 #pragma unroll
         for (int i = 0; i < NV; ++i) ys[i] = fma(fma(DP[A32], k2[i], DP[A31] * k1[i]), h, y[i]);
         rhs(th, ys, k3);
@@ -312,7 +368,9 @@ struct LorenzLanes {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const double part = fma(DP[E6], k6[i], fma(DP[E5], k5[i], fma(DP[E4], k4[i], fma(DP[E3], k3[i], DP[E1] * k1[i]))));
-            const double scale = fma(absmax_bits(y[i], ynew[i]), rtol, atol);
+            // max(|y|,|y_new|) as integer keys: the fp64 forms (DSETP + selects, or (|a|+|b|+||a|-|b||)/2) measured
+            // the same or slower (profiles/r2b_lorenz_ablation.txt)
+            const double scale = fma(absmax_bits(y[i], ynew[i]), rtol, i == 0 ? atol : atol_z);
             double r;
             asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(scale));
             r = fma(r, fma(-scale, r, 1.0), r);
@@ -327,7 +385,7 @@ struct LorenzLanes {
             if (i & 1) sb = fma(e, e, sb);
             else sa = fma(e, e, sa);
         }
-        return group_sum(sa + sb);
+        return group_sum_fast(sa + sb);
     }
 };
 
@@ -353,21 +411,25 @@ struct LorenzSolve {
 
     // solve_ivp(fun, (0,T), y0, 'RK45'): initial step (common.py:68-140), then steps until t == T.
     // `active`: this lane's chain takes part (others run predicated-off). All 32 lanes must call.
+    // FUSED numerics work in the scaled fast variables Z = s*Y between the first and the last line (state,
+    // derivatives and the three moment sums that contain Y_0); ratios to the error scale do not change because the
+    // absolute tolerance of a scaled variable is scaled with it.
     __device__ __forceinline__ void solve(const LorenzLanes<J, KT, NUM> &L, const LorenzDev &P, const LorenzTheta &th,
                                           bool active) {
         const double inv_sqrt_n = 1.0 / sqrt((double)P.nvar);
-        const double inv_n = 1.0 / (double)P.nvar;
+        const double atol_z = (NUM == LNUM_FUSED) ? P.atol * fabs(th.s) : P.atol;
         t = 0.0;
         n_t = n_acc = n_rej = 0;
 #pragma unroll
         for (int i = 0; i < 5; ++i) msum[i] = 0.0;
+        L.to_scaled(th, y);
         L.rhs(th, y, f);
         add_moments();  // t0 is stored too (lorenz_mcmc.py:68)
         {   // select_initial_step, direction = +1, order = 4
             double sc[NV], a0[NV], a1[NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
-                sc[i] = fma(fabs(y[i]), P.rtol, P.atol);
+                sc[i] = fma(fabs(y[i]), P.rtol, i == 0 ? P.atol : atol_z);
                 a0[i] = y[i] / sc[i];
                 a1[i] = f[i] / sc[i];
             }
@@ -389,8 +451,16 @@ struct LorenzSolve {
         done = !active || !(P.T > 0.0);
         step_rejected = false;
         new_step = true;
-        if (NUM == LNUM_FUSED) attempts_fused(L, P, th);
-        else attempts_exact(L, P, th);
+        if (NUM == LNUM_FUSED) {
+            attempts_fused(L, P, th, atol_z);
+            n_t = n_acc + 1;
+            L.from_scaled(th, y);
+            msum[1] *= th.inv_s;                 // sum Y_0
+            msum[3] *= th.inv_s;                 // sum X Y_0
+            msum[4] *= th.inv_s * th.inv_s;      // sum Y_0^2
+        } else {
+            attempts_exact(L, P, th);
+        }
     }
 
     // ---- RungeKutta._step_impl (rk.py:118-175), one attempt per iteration, scipy's order of operations
@@ -451,9 +521,18 @@ struct LorenzSolve {
     //  * the clamps of the controller (factor <= 10, <= 1 after a rejection, >= 0.2; rk.py:157-171) are
     //    predicates on the squared error norm evaluated beside the power -- 0.9 x^(-1/10) >= c  <=>
     //    x <= (0.9/c)^10 -- and select the exact clamp values afterwards;
-    //  * the power is rk_factor_fused (no F2F conversions, one 5-level Newton round);
-    //  * the 1/n of the RMS norm is folded into the thresholds (sum of squares ss = n e2).
-    __device__ __forceinline__ void attempts_fused(const LorenzLanes<J, KT, NUM> &L, const LorenzDev &P, const LorenzTheta &th) {
+    //  * the power is rk_hfactor_fused (no F2F conversions, one 5-level Newton round, h folded into its last FMA);
+    //  * the 1/n of the RMS norm is folded into the thresholds (sum of squares ss = n e2);
+    //  * behind the power there is ONE select (every special case -- the clamps, a step below min_step -- is
+    //    decided and its value formed beside the power), then the clip to t_bound as a compare of the new step
+    //    with T - t (known since the accept select) and a select: the first stage of the next attempt follows the
+    //    residual of the Newton round after FMA, select, DSETP, select.  scipy's h = (t + h_abs) - t
+    //    (rk.py:137-141) is taken as h_abs itself (they differ by the rounding of t + h_abs, ~1e-13 relative);
+    //  * a step below min_step (rk.py:122-131, never seen outside a failing integration) is not repaired in front
+    //    of the attempt but costs one idle attempt: the lane sits the attempt out, takes min_step (new step) or
+    //    fails (inside a step) afterwards -- the same sequence of steps as scipy, one pass later.
+    __device__ __forceinline__ void attempts_fused(const LorenzLanes<J, KT, NUM> &L, const LorenzDev &P, const LorenzTheta &th,
+                                                   double atol_z) {
         const double n = (double)P.nvar;
         const double inv_n = 1.0 / n;
         const double ss_one = n;                              // error_norm < 1
@@ -461,56 +540,68 @@ struct LorenzSolve {
         const double ss_cap1 = n * 0.3486784401;              // raw factor >= 1   <=> e2 <= 0.9^10
         const double ss_floor = n * 3405062.8916015625;       // raw factor <= 0.2 <=> e2 >= 4.5^10
         const float log2n_10 = 0.1f * log2f((float)P.nvar);
+        // Scheduling aid (no arithmetic effect): ptxas computes the accept predicate -- and with it the twenty accept
+        // selects -- only where it is first needed, i.e. BEHIND the power, although it is known ~100 cycles earlier.
+        // The seed of the power takes its bias from one of two identical registers picked by that predicate, which
+        // puts the predicate at the head of the critical chain and the selects into the idle slots of the power.
+        // (the twin differs only for a negative attempt budget, which never runs: a run-time fact ptxas cannot fold)
+        const float log2n_10_twin = log2n_10 + (P.max_attempts < 0 ? 1.0f : 0.0f);
         int guard = 0;
-        // min_step = 10 |nextafter(t) - t| (rk.py:122) depends on t alone: carried across the back edge and
-        // recomputed as soon as the accept select has produced t, off the chain factor -> h -> first stage
-        double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);      // t >= 0: no fabs
+        // the distance to t_bound depends on t alone: carried across the back edge and recomputed as soon as the
+        // accept select has produced t
+        double rem = P.T - t;
+        // the attempt in flight: its step and the state of its second stage (rotated loop)
+        double h = (h_abs > rem) ? rem : h_abs;               // t + h_abs beyond t_bound (rk.py:137-140); >= 0
+        double ys2[NV];
+        L.stage2(y, f, h, ys2);
         while (__any_sync(FULL, !done)) {
-            if (new_step) {
-                if (h_abs < min_step) h_abs = min_step;
-                step_rejected = false;
-            }
-            const bool fail = h_abs < min_step;
-            double t_new = t + h_abs;
-            const bool clip = t_new - P.T > 0.0;
-            t_new = clip ? P.T : t_new;
-            const bool last = !(t_new < P.T);                  // this attempt ends at t_bound (t_new <= T always)
-            const double h = t_new - t;                        // >= 0
             double ynew[NV], fnew[NV];
-            const double ss = L.attempt_fused(th, y, f, h, P.rtol, P.atol, ynew, fnew);
-            const bool live = !done && !fail;
+            const double ss = L.attempt_fused(th, y, f, ys2, h, P.rtol, P.atol, atol_z, ynew, fnew);
+            // flags and end time of this attempt (in source order behind it so that they share its basic block --
+            // the first shuffle of the loop body is preceded by a convergence check that ends the block at the loop top)
+            // min_step = 10 |nextafter(t) - t| (rk.py:122; t >= 0: no fabs)
+            const double min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);
+            const bool tiny = h_abs < min_step;               // off the chain: decides `live`
+            const double t_sum = t + h_abs;
+            const bool last = (h_abs > rem) || !(t_sum < P.T);   // this attempt ends at t_bound
+            const double t_new = last ? P.T : t_sum;
+            const bool live = !done && !tiny;
             const bool acc = live && (ss < ss_one);
             const bool rej = live && !acc;
-            // step factor: raw power beside its clamp predicates (NaN: no predicate holds except the last)
-            const double raw = rk_factor_fused(ss, inv_n, log2n_10);
+            // next step size: raw power beside its clamp predicates (NaN: no predicate holds except the floor)
             const bool at_cap = ss <= (step_rejected ? ss_cap1 : ss_cap10);   // incl. ss == 0 (rk.py:157-160)
             const bool at_floor = !(ss < ss_floor);                            // incl. NaN (max(0.2, nan) = 0.2)
-            double fac = at_cap ? (step_rejected ? 1.0 : RK_MAX_FACTOR) : raw;
-            fac = at_floor ? RK_MIN_FACTOR : fac;
-            h_abs = live ? h * fac : h_abs;
+            const double clamp_fac = at_floor ? RK_MIN_FACTOR : (step_rejected ? 1.0 : RK_MAX_FACTOR);
+            const double h_alt = tiny ? min_step : h * clamp_fac;
+            const bool use_alt = tiny || at_cap || at_floor;
+            const double h_raw = rk_hfactor_fused(ss, inv_n, acc ? log2n_10 : log2n_10_twin, h);
+            h_abs = use_alt ? h_alt : h_raw;
             // accept bookkeeping as selects
             t = acc ? t_new : t;
-            min_step = 10.0 * (__longlong_as_double(__double_as_longlong(t) + 1) - t);
+            rem = P.T - t;
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 y[i] = acc ? ynew[i] : y[i];
                 f[i] = acc ? fnew[i] : f[i];
             }
-            {
-                const double X = acc ? ynew[0] : 0.0, Y0 = (J > 0 && acc) ? ynew[1] : 0.0;
+            if (acc) {                                                // predicated fp64 instructions, no selects
+                const double X = ynew[0], Y0 = (J > 0) ? ynew[1] : 0.0;
                 msum[0] += X;
                 msum[1] += Y0;
                 msum[2] = fma(X, X, msum[2]);
                 msum[3] = fma(X, Y0, msum[3]);
                 msum[4] = fma(Y0, Y0, msum[4]);
             }
-            n_t += acc ? 1 : 0;
-            n_acc += acc ? 1 : 0;
+            n_acc += acc ? 1 : 0;                             // n_t = n_acc + 1 (t0 is stored too) after the loop
             n_rej += rej ? 1 : 0;
+            const bool fail = tiny && !new_step;               // TOO_SMALL_STEP inside a step: solve_ivp stops
             new_step = acc || (new_step && !rej);
-            step_rejected = rej || step_rejected;             // cleared at the top of the next new step
+            step_rejected = !new_step && (rej || step_rejected);   // a new step starts with the flag cleared
             ++guard;
             done = done || fail || guard >= P.max_attempts || (acc && last);
+            // the next attempt: its step and second stage
+            h = (h_abs > rem) ? rem : h_abs;
+            L.stage2(y, f, h, ys2);
         }
     }
 };

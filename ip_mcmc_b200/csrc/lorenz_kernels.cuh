@@ -325,7 +325,9 @@ __global__ void __launch_bounds__(32) lorenz_rhs_kernel(int K, long long n, cons
             th = LorenzTheta{theta[4 * c], theta[4 * c + 1], theta[4 * c + 2], theta[4 * c + 3], 0, 0};
         }
         th.finish(J);
+        L.to_scaled(th, y);      // FUSED numerics: the right-hand side of the scaled fast variables (lorenz.cuh)
         L.rhs(th, y, dy);
+        L.from_scaled(th, dy);
         if (active) lorenz_store_state<J, KT, NUM>(L, out + c * nvar, dy);
     }
 }
@@ -356,9 +358,18 @@ __global__ void __launch_bounds__(32) lorenz_attempt_kernel(int K, long long n, 
             h = hstep[c];
         }
         th.finish(J);
+        L.to_scaled(th, y);
         L.rhs(th, y, f);
-        const double ss = (NUM == LNUM_FUSED) ? L.attempt_fused(th, y, f, h, rtol, atol, yn, fn)
-                                              : L.attempt(th, y, f, h, rtol, atol, yn, fn);
+        double ss;
+        if (NUM == LNUM_FUSED) {
+            double ys2[J + 1];
+            L.stage2(y, f, h, ys2);
+            ss = L.attempt_fused(th, y, f, ys2, h, rtol, atol, atol * fabs(th.s), yn, fn);
+        } else {
+            ss = L.attempt(th, y, f, h, rtol, atol, yn, fn);
+        }
+        L.from_scaled(th, yn);
+        L.from_scaled(th, fn);
         const double err = sqrt(ss) * inv_sqrt_n;
         if (active) {
             double *o = out + c * (2 * nvar + 1);
