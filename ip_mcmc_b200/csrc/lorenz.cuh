@@ -14,6 +14,10 @@
 #include "common.cuh"
 
 // developer switch for A/B measurements (tools/build_lorenz_variants.py): the two-level group sum of the FUSED path
+// max(|y|,|y_new|) of the FUSED error scale as DSETP on |.| operands + one 64-bit select (1) or as integer keys (0)
+#ifndef IPMCMC_LORENZ_ABSMAX_DSETP
+#define IPMCMC_LORENZ_ABSMAX_DSETP 1
+#endif
 #ifndef IPMCMC_LORENZ_GSUM2
 #define IPMCMC_LORENZ_GSUM2 1
 #endif
@@ -211,6 +215,9 @@ struct LorenzLanes {
     //   dZ_j = s*dY_j = Z_{j+1}*(Z_{j+2} - Z_{j-1}) - c*Z_j + (s*c*h/J) X  = fma(Z_{j+1}, Z_{j+2}-Z_{j-1}, fma(-c, Z_j, sA*X))
     //   dX   = F - X - X_{k-1}*(X_{k-2} - X_{k+1}) - (hc/J) sum_j Y_j,   (hc/J) sum Y = -mS * sum Z
     // y[0] = X_k, y[1+j] = Z_{k,j}; dy likewise (d/dt of the scaled variables).
+    // C10: the time-scale ratio c is the reference's 10 (lorenz_mcmc.py:84): -c enters the FMA as an immediate (two
+    // register operands, a two-cycle issue) instead of a register the compiler cannot keep uniform beside the tableau.
+    template <bool C10 = false>
     __device__ __forceinline__ void rhs_fused(const LorenzTheta &th, const double (&y)[NV], double (&dy)[NV]) const {
         const double X = y[0];
         const double Xm1 = __shfl_sync(FULL, X, src_m1);
@@ -229,7 +236,7 @@ struct LorenzLanes {
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const double e = y[1 + (j + 2) % J] - y[1 + (j + J - 1) % J];
-                dy[1 + j] = fma(y[1 + (j + 1) % J], e, fma(-th.c, y[1 + j], A));
+                dy[1 + j] = fma(y[1 + (j + 1) % J], e, C10 ? fma(-10.0, y[1 + j], A) : fma(-th.c, y[1 + j], A));
             }
             out = fma(th.mS, t[0], out);
         }
@@ -338,39 +345,44 @@ struct LorenzLanes {
 #pragma unroll
         for (int i = 0; i < NV; ++i) ys2[i] = fma(DP[A21] * k1[i], h, y[i]);
     }
+    template <bool C10 = false>
     __device__ __forceinline__ double attempt_fused(const LorenzTheta &th, const double (&y)[NV], const double (&k1)[NV],
                                                     const double (&ys2)[NV], double h, double rtol, double atol,
                                                     double atol_z, double (&ynew)[NV], double (&k7)[NV]) const {
         double k2[NV], k3[NV], k4[NV], k5[NV], k6[NV], ys[NV];
-        rhs(th, ys2, k2);
+        rhs_fused<C10>(th, ys2, k2);
 #pragma unroll
         for (int i = 0; i < NV; ++i) ys[i] = fma(fma(DP[A32], k2[i], DP[A31] * k1[i]), h, y[i]);
-        rhs(th, ys, k3);
+        rhs_fused<C10>(th, ys, k3);
 #pragma unroll
         for (int i = 0; i < NV; ++i) ys[i] = fma(fma(DP[A43], k3[i], fma(DP[A42], k2[i], DP[A41] * k1[i])), h, y[i]);
-        rhs(th, ys, k4);
+        rhs_fused<C10>(th, ys, k4);
 #pragma unroll
         for (int i = 0; i < NV; ++i)
             ys[i] = fma(fma(DP[A54], k4[i], fma(DP[A53], k3[i], fma(DP[A52], k2[i], DP[A51] * k1[i]))), h, y[i]);
-        rhs(th, ys, k5);
+        rhs_fused<C10>(th, ys, k5);
 #pragma unroll
         for (int i = 0; i < NV; ++i)
             ys[i] = fma(fma(DP[A65], k5[i],
                             fma(DP[A64], k4[i], fma(DP[A63], k3[i], fma(DP[A62], k2[i], DP[A61] * k1[i])))),
                         h, y[i]);
-        rhs(th, ys, k6);
+        rhs_fused<C10>(th, ys, k6);
 #pragma unroll
         for (int i = 0; i < NV; ++i)
             ynew[i] = fma(h, fma(DP[B6], k6[i], fma(DP[B5], k5[i], fma(DP[B4], k4[i], fma(DP[B3], k3[i], DP[B1] * k1[i])))),
                           y[i]);
-        rhs(th, ynew, k7);
+        rhs_fused<C10>(th, ynew, k7);
         double S[NV], Q[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const double part = fma(DP[E6], k6[i], fma(DP[E5], k5[i], fma(DP[E4], k4[i], fma(DP[E3], k3[i], DP[E1] * k1[i]))));
-            // max(|y|,|y_new|) as integer keys: the fp64 forms (DSETP + selects, or (|a|+|b|+||a|-|b||)/2) measured
-            // the same or slower (profiles/r2b_lorenz_ablation.txt)
+#if IPMCMC_LORENZ_ABSMAX_DSETP
+            // 15 instead of 36 instructions for the five maxima (a NaN y_new is selected and poisons the norm, as it must)
+            const double ym = (fabs(y[i]) > fabs(ynew[i])) ? y[i] : ynew[i];
+            const double scale = fma(fabs(ym), rtol, i == 0 ? atol : atol_z);
+#else
             const double scale = fma(absmax_bits(y[i], ynew[i]), rtol, i == 0 ? atol : atol_z);
+#endif
             double r;
             asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(scale));
             r = fma(r, fma(-scale, r, 1.0), r);
@@ -452,7 +464,8 @@ struct LorenzSolve {
         step_rejected = false;
         new_step = true;
         if (NUM == LNUM_FUSED) {
-            attempts_fused(L, P, th, atol_z);
+            if (P.c == 10.0) attempts_fused<true>(L, P, th, atol_z);   // kernel parameter: warp-uniform
+            else attempts_fused<false>(L, P, th, atol_z);
             n_t = n_acc + 1;
             L.from_scaled(th, y);
             msum[1] *= th.inv_s;                 // sum Y_0
@@ -531,6 +544,7 @@ struct LorenzSolve {
     //  * a step below min_step (rk.py:122-131, never seen outside a failing integration) is not repaired in front
     //    of the attempt but costs one idle attempt: the lane sits the attempt out, takes min_step (new step) or
     //    fails (inside a step) afterwards -- the same sequence of steps as scipy, one pass later.
+    template <bool C10>
     __device__ __forceinline__ void attempts_fused(const LorenzLanes<J, KT, NUM> &L, const LorenzDev &P, const LorenzTheta &th,
                                                    double atol_z) {
         const double n = (double)P.nvar;
@@ -556,7 +570,7 @@ struct LorenzSolve {
         L.stage2(y, f, h, ys2);
         while (__any_sync(FULL, !done)) {
             double ynew[NV], fnew[NV];
-            const double ss = L.attempt_fused(th, y, f, ys2, h, P.rtol, P.atol, atol_z, ynew, fnew);
+            const double ss = L.template attempt_fused<C10>(th, y, f, ys2, h, P.rtol, P.atol, atol_z, ynew, fnew);
             // flags and end time of this attempt (in source order behind it so that they share its basic block --
             // the first shuffle of the loop body is preceded by a convergence check that ends the block at the loop top)
             // min_step = 10 |nextafter(t) - t| (rk.py:122; t >= 0: no fabs)
