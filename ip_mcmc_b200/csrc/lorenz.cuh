@@ -215,9 +215,10 @@ struct LorenzLanes {
     //   dZ_j = s*dY_j = Z_{j+1}*(Z_{j+2} - Z_{j-1}) - c*Z_j + (s*c*h/J) X  = fma(Z_{j+1}, Z_{j+2}-Z_{j-1}, fma(-c, Z_j, sA*X))
     //   dX   = F - X - X_{k-1}*(X_{k-2} - X_{k+1}) - (hc/J) sum_j Y_j,   (hc/J) sum Y = -mS * sum Z
     // y[0] = X_k, y[1+j] = Z_{k,j}; dy likewise (d/dt of the scaled variables).
-    // C10: the time-scale ratio c is the reference's 10 (lorenz_mcmc.py:84): -c enters the FMA as an immediate (two
-    // register operands, a two-cycle issue) instead of a register the compiler cannot keep uniform beside the tableau.
-    template <bool C10 = false>
+    // C1: the time-scale ratio c is the reference's 1 (lorenz_mcmc.py:91, theta = [F, h, c, b] = [10, 10, 1, 10]):
+    // -c*Z_j + A is the subtraction A - Z_j (same bits as the FMA with c = 1; two register operands, a two-cycle
+    // issue) instead of an FMA with c in a register that the compiler cannot keep uniform beside the tableau.
+    template <bool C1 = false>
     __device__ __forceinline__ void rhs_fused(const LorenzTheta &th, const double (&y)[NV], double (&dy)[NV]) const {
         const double X = y[0];
         const double Xm1 = __shfl_sync(FULL, X, src_m1);
@@ -236,7 +237,7 @@ struct LorenzLanes {
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 const double e = y[1 + (j + 2) % J] - y[1 + (j + J - 1) % J];
-                dy[1 + j] = fma(y[1 + (j + 1) % J], e, C10 ? fma(-10.0, y[1 + j], A) : fma(-th.c, y[1 + j], A));
+                dy[1 + j] = fma(y[1 + (j + 1) % J], e, C1 ? (A - y[1 + j]) : fma(-th.c, y[1 + j], A));
             }
             out = fma(th.mS, t[0], out);
         }
@@ -345,33 +346,33 @@ struct LorenzLanes {
 #pragma unroll
         for (int i = 0; i < NV; ++i) ys2[i] = fma(DP[A21] * k1[i], h, y[i]);
     }
-    template <bool C10 = false>
+    template <bool C1 = false>
     __device__ __forceinline__ double attempt_fused(const LorenzTheta &th, const double (&y)[NV], const double (&k1)[NV],
                                                     const double (&ys2)[NV], double h, double rtol, double atol,
                                                     double atol_z, double (&ynew)[NV], double (&k7)[NV]) const {
         double k2[NV], k3[NV], k4[NV], k5[NV], k6[NV], ys[NV];
-        rhs_fused<C10>(th, ys2, k2);
+        rhs_fused<C1>(th, ys2, k2);
 #pragma unroll
         for (int i = 0; i < NV; ++i) ys[i] = fma(fma(DP[A32], k2[i], DP[A31] * k1[i]), h, y[i]);
-        rhs_fused<C10>(th, ys, k3);
+        rhs_fused<C1>(th, ys, k3);
 #pragma unroll
         for (int i = 0; i < NV; ++i) ys[i] = fma(fma(DP[A43], k3[i], fma(DP[A42], k2[i], DP[A41] * k1[i])), h, y[i]);
-        rhs_fused<C10>(th, ys, k4);
+        rhs_fused<C1>(th, ys, k4);
 #pragma unroll
         for (int i = 0; i < NV; ++i)
             ys[i] = fma(fma(DP[A54], k4[i], fma(DP[A53], k3[i], fma(DP[A52], k2[i], DP[A51] * k1[i]))), h, y[i]);
-        rhs_fused<C10>(th, ys, k5);
+        rhs_fused<C1>(th, ys, k5);
 #pragma unroll
         for (int i = 0; i < NV; ++i)
             ys[i] = fma(fma(DP[A65], k5[i],
                             fma(DP[A64], k4[i], fma(DP[A63], k3[i], fma(DP[A62], k2[i], DP[A61] * k1[i])))),
                         h, y[i]);
-        rhs_fused<C10>(th, ys, k6);
+        rhs_fused<C1>(th, ys, k6);
 #pragma unroll
         for (int i = 0; i < NV; ++i)
             ynew[i] = fma(h, fma(DP[B6], k6[i], fma(DP[B5], k5[i], fma(DP[B4], k4[i], fma(DP[B3], k3[i], DP[B1] * k1[i])))),
                           y[i]);
-        rhs_fused<C10>(th, ynew, k7);
+        rhs_fused<C1>(th, ynew, k7);
         double S[NV], Q[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
@@ -464,7 +465,7 @@ struct LorenzSolve {
         step_rejected = false;
         new_step = true;
         if (NUM == LNUM_FUSED) {
-            if (P.c == 10.0) attempts_fused<true>(L, P, th, atol_z);   // kernel parameter: warp-uniform
+            if (P.c == 1.0) attempts_fused<true>(L, P, th, atol_z);   // kernel parameter: warp-uniform
             else attempts_fused<false>(L, P, th, atol_z);
             n_t = n_acc + 1;
             L.from_scaled(th, y);
@@ -544,7 +545,7 @@ struct LorenzSolve {
     //  * a step below min_step (rk.py:122-131, never seen outside a failing integration) is not repaired in front
     //    of the attempt but costs one idle attempt: the lane sits the attempt out, takes min_step (new step) or
     //    fails (inside a step) afterwards -- the same sequence of steps as scipy, one pass later.
-    template <bool C10>
+    template <bool C1>
     __device__ __forceinline__ void attempts_fused(const LorenzLanes<J, KT, NUM> &L, const LorenzDev &P, const LorenzTheta &th,
                                                    double atol_z) {
         const double n = (double)P.nvar;
@@ -570,7 +571,7 @@ struct LorenzSolve {
         L.stage2(y, f, h, ys2);
         while (__any_sync(FULL, !done)) {
             double ynew[NV], fnew[NV];
-            const double ss = L.template attempt_fused<C10>(th, y, f, ys2, h, P.rtol, P.atol, atol_z, ynew, fnew);
+            const double ss = L.template attempt_fused<C1>(th, y, f, ys2, h, P.rtol, P.atol, atol_z, ynew, fnew);
             // flags and end time of this attempt (in source order behind it so that they share its basic block --
             // the first shuffle of the loop body is preceded by a convergence check that ends the block at the loop top)
             // min_step = 10 |nextafter(t) - t| (rk.py:122; t >= 0: no fabs)

@@ -127,6 +127,29 @@ def test_short_solves_vs_reference(G, numerics):
         np.testing.assert_allclose(r["state"].cpu().numpy()[0], gs[f"case{i}_IC_end"], rtol=0, atol=100 * tol)
 
 
+@pytest.mark.parametrize("numerics", ["exact", "fused"])
+@pytest.mark.parametrize("c", [1.0, 3.0])
+def test_short_solves_other_time_scale_ratio_and_small_b(G, numerics, c):
+    """FUSED integrates the scaled fast variables Z = -b c Y and specialises c = 1 (the reference's value): the
+    general-c code path, and parameters with b close to zero (scale clamped at 1e-30, a linear fast system), against
+    the oracle's solve_ivp restatement: same step counts, G and end state to 1e-9."""
+    import ip_mcmc_b200 as M
+    p = golden("lorenz_problem_K6_J4.npz")
+    T = 0.25
+    us = [np.array([-1.9, 1.9, 0.9]), np.array([0.5, -2.0, -3.0]),
+          -p["prior_means"] + np.array([9.0, 8.0, 1e-9]),      # b = 1e-9
+          -p["prior_means"] + np.array([11.0, 9.0, 0.0])]      # b = 0: the quadratic term vanishes
+    for u in us:
+        f = M.Lorenz96Moments(6, 4, T, c, p["prior_means"], p["IC"], numerics=numerics)
+        op = L.LorenzProblem(6, 4, T, c, p["prior_means"], p["IC"])
+        r = f.batch(u.reshape(1, 3), p["IC"].reshape(1, -1))
+        g_ref = op(u)
+        acc, rej = r["work"][0].tolist()
+        assert (acc, rej) == (op.n_accepted, op.n_rejected), (c, u)
+        np.testing.assert_allclose(r["G"].cpu().numpy()[0], g_ref, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(r["state"].cpu().numpy()[0], op.IC, rtol=0, atol=1e-8)
+
+
 def test_stateful_operator_and_potential_semantics(G):
     """LorenzObservationOperator carries its IC (lorenz_mcmc.py:66): two successive calls differ
     and equal one solve continued from the first end state; Phi matches the oracle's logpdf."""
