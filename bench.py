@@ -5,7 +5,8 @@
     torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, NCCL)
 
 A "step" is ONE launch of the fused kernel advancing every chain of the batch by `--mcmc-steps`
-Metropolis steps (proposal -> forward solve -> Phi -> accept/reject -> moments).  Workloads
+Metropolis steps (proposal -> forward solve -> Phi -> accept/reject -> moments; default 1000 / 16 / 128 steps per
+launch for the three workloads, see WORKLOADS).  Workloads
 (BASELINE.json `configs`):
     burgers_pcn_256   configs[2]: Burgers pCN beta=0.25, 1024 chains x 256 cells per GPU   (default)
     burgers_pcn_1024  configs[3]: Burgers pCN, 8192 chains x 1024 cells per GPU (65536 over 8 GPUs)
@@ -35,11 +36,18 @@ if ROOT not in sys.path:
 TRUTH = np.array([0.025, -0.025, -0.02])
 PRIOR_MEAN = np.array([1.5, 0.25, -0.5])
 
+# Metropolis steps per launch (= per bench "step").  MCMCSampler.run(n_steps) is ONE launch whatever n_steps is, and the
+# reference's chains are 5000+ steps long; a launch ends when its slowest chain ends, and with as many resident warps as
+# chains nothing can be rebalanced at the end, so short launches pay the spread of per-chain work once per launch
+# (1024 x 256 cells: 200-step launches 70.9 %, 1000-step launches 74.0 % of the DFMA peak, 5000 steps 74.8 %).
+# Round 1 and the first half of round 2 timed 200 / 4 / 32 steps per launch; that figure is still reported
+# (`short_launch`).
 WORKLOADS = {
-    "burgers_pcn_256": dict(model="burgers", N=256, chains=1024, mcmc_steps=200, beta=0.25),
-    "burgers_pcn_1024": dict(model="burgers", N=1024, chains=8192, mcmc_steps=4, beta=0.25),
-    "lorenz_rw": dict(model="lorenz", chains=4096, mcmc_steps=32, delta=0.125, T=20.0),
+    "burgers_pcn_256": dict(model="burgers", N=256, chains=1024, mcmc_steps=1000, beta=0.25),
+    "burgers_pcn_1024": dict(model="burgers", N=1024, chains=8192, mcmc_steps=16, beta=0.25),
+    "lorenz_rw": dict(model="lorenz", chains=4096, mcmc_steps=128, delta=0.125, T=20.0),
 }
+SHORT_LAUNCH_STEPS = 200
 
 
 # ------------------------------------------------------------------------------------------------
@@ -486,7 +494,7 @@ def main():
         # the other BASELINE.json configs, at EVERY N (weak scaling: the same per-GPU batch on every rank)
         plan = [("lorenz_rw", dict(WORKLOADS["lorenz_rw"]), 0, True),
                 ("burgers_pcn_1024", dict(WORKLOADS["burgers_pcn_1024"]), 100, False),
-                ("burgers_pcn_256_exact", dict(WORKLOADS["burgers_pcn_256"], numerics="exact", mcmc_steps=100), 400, False)]
+                ("burgers_pcn_256_exact", dict(WORKLOADS["burgers_pcn_256"], numerics="exact", mcmc_steps=200), 400, False)]
         for name, w, b_in, e2e in plan:
             r = measure(w, 3, 3, with_e2e=e2e, trace_chains=8, burn_in=b_in,
                         start=(TRUTH - PRIOR_MEAN) if w["model"] == "burgers" else None)
@@ -502,6 +510,13 @@ def main():
                 if k in r:
                     extra[name][k] = r[k]
         cold = cold_start(dict(wl), 5000, 3)
+    short = None
+    if not args.no_extra and args.workload == "burgers_pcn_256" and wl["mcmc_steps"] > SHORT_LAUNCH_STEPS:
+        # the same workload in 200-step launches (what rounds 1 and 2a timed): the launch tail is paid 5x as often
+        r = measure(dict(wl, mcmc_steps=SHORT_LAUNCH_STEPS), 5, 3, with_e2e=False, trace_chains=8, burn_in=burn_in, start=start)
+        short = dict(chain_steps_per_sec=r["value"], roofline_tflops=r["achieved"], roofline_frac=r["achieved"] / peak,
+                     roofline_frac_nominal=r["achieved"] / nominal_fp64, ms_per_step=r["total_ms"] / 5,
+                     mcmc_steps_per_launch=SHORT_LAUNCH_STEPS)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -537,7 +552,8 @@ def main():
                 kernel_ms_per_step=[round(x, 3) for x in res["kern_ms"]],
                 per_rank_ms=dict(columns=["sum_kernel", "final_reduce", "wall_timed_region", "sm_mhz", "n_throttle_reasons",
                                           "slowest_launch", "fastest_launch"], rows=res["per_rank"]),
-                posterior_mean=[float(x) for x in res["pooled"][1:4]], cold_start=cold, extra_workloads=extra)
+                posterior_mean=[float(x) for x in res["pooled"][1:4]], cold_start=cold, short_launch=short,
+                extra_workloads=extra)
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         line.update(cpu_baselines(wl, cores))
