@@ -313,6 +313,10 @@ int ipmcmc_lorenz_rk45_attempt(int32_t K, int32_t J, int32_t numerics, int64_t n
 /* Engine RNG: out_dev [n_chains, n_steps, d + 1] = (normals xi_0..xi_{d-1}, uniform U). */
 int ipmcmc_rng_probe(uint64_t seed, int64_t chain_offset, int64_t first_step, int64_t n_chains,
                      int64_t n_steps, int32_t dim, double *out_dev, void *stream);
+/* The branch-free IEEE division of the EXACT positive-monotone Burgers loop (dt = (dx/2) / max|u|, rusanov.py:102-109)
+   beside the compiler's:  q_fast_dev[i] = div_rn_fast(a, b_dev[i]),  q_ieee_dev[i] = a / b_dev[i]  (must be the same
+   bits for 1e-100 < b < 1e100). */
+int ipmcmc_div_probe(int64_t n, double a, const double *b_dev, double *q_fast_dev, double *q_ieee_dev, void *stream);
 /* Dependent-free DFMA micro-benchmark: returns measured fp64 FMA throughput in TFLOP/s
    (2 flops per FMA) of the current device, timed with CUDA events over `iters` launches.  */
 int ipmcmc_fp64_peak(int32_t iters, double *tflops_out);

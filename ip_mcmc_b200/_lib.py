@@ -88,6 +88,7 @@ SYMBOLS = {
                                     C.c_void_p]),
     "ipmcmc_lorenz_rk45_attempt": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "ipmcmc_div_probe": (C.c_int, [C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ipmcmc_rng_probe": (C.c_int, [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                    C.c_void_p, C.c_void_p]),
     "ipmcmc_fp64_peak": (C.c_int, [C.c_int32, c_double_p]),

@@ -776,6 +776,22 @@ __global__ void rng_probe_kernel(unsigned long long seed, long long chain_offset
     }
 }
 
+__global__ void div_probe_kernel(long long n, double a, const double *__restrict__ b, double *__restrict__ qf,
+                                 double *__restrict__ qi) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        bool ok;
+        qf[i] = BurgersWarp<1, NUM_EXACT, false>::div_rn_fast(a, b[i], ok);
+        qi[i] = a / b[i];
+    }
+}
+extern "C" int ipmcmc_div_probe(int64_t n, double a, const double *b_dev, double *q_fast_dev, double *q_ieee_dev, void *stream) {
+    if (!b_dev || !q_fast_dev || !q_ieee_dev) return fail(IPMCMC_EINVAL, "NULL argument");
+    if (n <= 0) return 0;
+    div_probe_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(n, a, b_dev, q_fast_dev, q_ieee_dev);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int ipmcmc_rng_probe(uint64_t seed, int64_t chain_offset, int64_t first_step, int64_t n_chains,
                                 int64_t n_steps, int32_t dim, double *out_dev, void *stream) {
     if (!out_dev || dim < 1) return fail(IPMCMC_EINVAL, "bad argument");

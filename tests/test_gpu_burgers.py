@@ -150,6 +150,44 @@ def test_monotone_cfl_shortcut_is_bit_identical(G, N):
     assert a["work"][:, 0].max().item() == 8 * N + 256          # some blow-up solves hit the cap in both
 
 
+@pytest.mark.parametrize("N", [64, 100, 256, 1000, 1024])
+def test_exact_positive_monotone_shortcut_is_bit_identical(G, N):
+    """EXACT numerics (the API default) run positive states that are monotone in x through a loop that takes max|u|
+    from the upstream end cell and the larger |h| of two neighbours from the direction of the profile, guarded by
+    the signs of every difference, and divides without the compiler's slow-path branch (burgers.cuh,
+    time_loop_exact_mono).  With the shortcut switched off every solve runs the general code: G, Phi, the end state
+    and the FV step count must be the same bits (the golden fixtures pin both to the reference)."""
+    import ip_mcmc_b200 as M
+    rng = np.random.default_rng(N + 1)
+    n = 1024 if N <= 256 else 128
+    u = 0.25 * rng.standard_normal((n, 3))
+    u[: n // 4, 2] = rng.uniform(-0.55, 1.55, n // 4)
+    u[n // 4: n // 2, 0] = rng.uniform(-2.4, -1.0, n // 4)  # left state below the right one: non-decreasing profiles
+    u[0] = [0.3, -0.2, (-1 - 0.5 / N) + 0.5]         # jump between the left ghost and the first cell centre: blow-up
+    u[1] = [-1.0, 0.25, 0.0]                          # constant state 1.5 (both directions hold)
+    a = M.BurgersFVM(N=N, numerics="exact").batch(u, want_state=True)
+    b = M.BurgersFVM(N=N, numerics="exact", monotone_shortcut=False).batch(u, want_state=True)
+    for k in ("G", "phi", "state", "work"):
+        assert np.array_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), equal_nan=True), k
+
+
+def test_branch_free_division_is_ieee(G):
+    """dt = (dx/2) / max|u| of the EXACT positive-monotone loop: the branch-free sequence against the compiler's
+    division, bit for bit, over 4M denominators (log-uniform over 12 decades, neighbours of powers of two, ties)."""
+    from ip_mcmc_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(7)
+    b = np.concatenate([10.0 ** rng.uniform(-6, 6, 1 << 22),
+                        np.nextafter(2.0 ** np.arange(-20, 21), np.inf), np.nextafter(2.0 ** np.arange(-20, 21), 0),
+                        2.0 ** np.arange(-20.0, 21.0), [3.0, 1.0 / 3.0, 2.525, 0.225, 1e-99, 1e99]])
+    bt = G.cuda(b)
+    for a in (1.0 / 64, 1.0 / 100, 1.0 / 256, 1.0 / 1000, 1.0 / 1024, 0.1):
+        qf, qi = torch.empty_like(bt), torch.empty_like(bt)
+        _lib.check(lib.ipmcmc_div_probe(b.size, a, bt.data_ptr(), qf.data_ptr(), qi.data_ptr(), None))
+        assert torch.equal(qf, qi), a
+        assert np.array_equal(qi.cpu().numpy(), a / b)          # and both are the host's IEEE quotient
+
+
 def test_callable_interfaces_match_reference_semantics(G):
     """observation_operator(u) -> ndarray[q]; potential(u) -> float (potential.py:53-54)."""
     g = golden("burgers_forward_N64.npz")
