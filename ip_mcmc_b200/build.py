@@ -11,11 +11,14 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libipmcmc.so")
 OBJ = os.path.join(PKG, "_build")
-# Translation units: the C ABI + Lorenz + small kernels, and the Burgers kernels once per cells-per-lane
-# value (0 = the team kernels for 2048 / 4096 cells).  They compile in parallel, and an edit to one kernel
-# family cannot move ptxas' schedule of another.
-UNITS = [("engine", "engine.cu", [])] + [("burgers_cpl%d" % c, "burgers_inst.cu", ["-DIPMCMC_TU_CPL=%d" % c])
-                                         for c in (32, 16, 8, 7, 4, 2, 1, 0)]
+# Translation units: the C ABI + Lorenz + small kernels, and the Burgers kernels once per cells-per-lane value AND
+# numerics (0 = the team kernels for 2048 / 4096 cells, one unit).  They compile in parallel, and an edit to one kernel
+# family cannot move the code generated for another: with EXACT and FUSED in one unit, an edit to EXACT-only templates
+# changed the inlining of the FUSED chain kernel (round 2; the split units reproduce the measured FUSED SASS bit for bit).
+UNITS = ([("engine", "engine.cu", [])]
+         + [("burgers_cpl%d_%s" % (c, "fused" if num else "exact"), "burgers_inst.cu",
+             ["-DIPMCMC_TU_CPL=%d" % c, "-DIPMCMC_TU_NUM=%d" % num]) for c in (32, 16, 8, 7, 4, 2, 1) for num in (1, 0)]
+         + [("burgers_cpl0", "burgers_inst.cu", ["-DIPMCMC_TU_CPL=0"])])
 SOURCES = ["engine.cu", "burgers_inst.cu"]
 HEADERS = ["common.cuh", "philox.cuh", "burgers.cuh", "burgers_kernels.cuh", "burgers_team.cuh", "burgers_launch.cuh",
            "burgers_launch_impl.cuh", "lorenz.cuh", "lorenz_kernels.cuh", "sampler.cuh",

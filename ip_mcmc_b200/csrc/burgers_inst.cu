@@ -1,6 +1,6 @@
 // Explicit instantiations of the Burgers launchers (and with them the kernels) for ONE cells-per-lane
-// value: compiled as  nvcc -DIPMCMC_TU_CPL=<1|2|4|7|8|16|32> -c burgers_inst.cu  (0 = the team kernels for
-// 2048 / 4096 cells), see ip_mcmc_b200/build.py.
+// value and ONE numerics: compiled as  nvcc -DIPMCMC_TU_CPL=<1|2|4|7|8|16|32> -DIPMCMC_TU_NUM=<0 exact|1 fused>
+// -c burgers_inst.cu  (CPL 0 = the team kernels for 2048 / 4096 cells, both numerics), see ip_mcmc_b200/build.py.
 #include "burgers_launch_impl.cuh"
 
 #ifndef IPMCMC_TU_CPL
@@ -26,10 +26,14 @@ namespace ipmcmc {
     template cudaError_t burgers_launch_wide_chain<IPMCMC_TU_CPL, NUM, PAD>(const BurgersDev &, const SamplerDev &,     \
                                                                             const ChainBufDev &, long long, long long, \
                                                                             cudaStream_t);
+#if !defined(IPMCMC_TU_NUM) || IPMCMC_TU_NUM == 0
 INST(NUM_EXACT, false)
 INST(NUM_EXACT, true)
+#endif
+#if !defined(IPMCMC_TU_NUM) || IPMCMC_TU_NUM == 1
 INST(NUM_FUSED, false)
 INST(NUM_FUSED, true)
+#endif
 #else
 #define INST(NUM, TM)                                                                                             \
     template cudaError_t burgers_launch_team_forward<NUM, TM>(const BurgersDev &, long long, const double *, double *, \
