@@ -57,6 +57,7 @@ struct BurgersTeam {
 
     // ---- FUSED ------------------------------------------------------------------------------
     bool positive, monotone;   // CTA-uniform, decided after the first time step (decide())
+    bool mono_ok;              // end-of-solve guard of the monotone shortcut (set at the end of fused_loop)
 
     template <bool POS>
     __device__ __forceinline__ void flux_fused(const double (&w)[CPL], double wL, double wR, bool left_general,
@@ -235,6 +236,9 @@ struct BurgersTeam {
             ++n;
         }
         capped = t < C.T;
+        // the guard of the monotone shortcut is evaluated HERE, so that `monotone` / `positive` are dead behind the
+        // dispatch and hold no predicate register across the time loop (burgers.cuh, time_loop_mono)
+        mono_ok = !MONO || capped || mono_end_ok(X, tw, lane);
         return n;
     }
 
@@ -243,6 +247,7 @@ struct BurgersTeam {
         double t = 0.0;   // every warp of the team computes the same dt, hence the same trip count
         int n = 0;
         positive = monotone = false;
+        mono_ok = true;
         if (NUMERICS == NUM_FUSED) {
             if (t < C.T && n < C.max_fv_steps) {
                 t += step_fused<true, false, false>(C, X, tw, lane);
@@ -305,7 +310,7 @@ struct BurgersTeam {
             const bool allow_mono = pass == 0 && !B.no_mono;
             if (NUMERICS == NUM_FUSED || B.dx_pow2) n = time_loop<true>(C, X, tw, lane, allow_mono);
             else n = time_loop<false>(C, X, tw, lane, allow_mono);
-            if (!(NUMERICS == NUM_FUSED && monotone && !capped) || mono_end_ok(X, tw, lane)) break;
+            if (mono_ok) break;
         }
         return n;
     }
