@@ -662,6 +662,28 @@ static bool uses_queue(const ipmcmc_problem *p) {
     return p->model == IPMCMC_MODEL_LORENZ || (p->b.N <= 1024 && p->b.d <= IPMCMC_MAX_DIM);
 }
 
+// The arena of ipmcmc_sample_host comes from a pool of the library's own (one per device) that keeps its memory
+// between calls: with the default pool's release threshold of zero every call paid the physical allocation of the
+// whole arena again (tens of milliseconds for a 25 MB sample buffer, and the reason the C entry point's end-to-end
+// figure varied from run to run).
+static cudaMemPool_t arena_pool() {
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t mp = nullptr;
+        if (cudaMemPoolCreate(&mp, &props) != cudaSuccess) return nullptr;
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+        pools[dev] = mp;
+    }
+    return pools[dev];
+}
+
 extern "C" int ipmcmc_sample_host(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, int64_t n_chains, int64_t n_steps,
                                   const ipmcmc_host_io *io, void *stream) {
     if (!p || !s || !io || !io->u0_host) return fail(IPMCMC_EINVAL, "NULL argument");
@@ -682,7 +704,10 @@ extern "C" int ipmcmc_sample_host(ipmcmc_problem *p, const ipmcmc_sampler_desc *
     const size_t n_sched = queue ? (size_t)sched_len((long long)units) : 0;
     const size_t pool_bytes = (size_t)ipmcmc_pool_scratch_bytes(n_chains, d);
     double *arena = nullptr;
-    CUDA_TRY(cudaMallocAsync((void **)&arena, n_dbl * sizeof(double) + (B * CNT_N + n_sched) * sizeof(long long) + pool_bytes, st));
+    cudaMemPool_t mem_pool = arena_pool();
+    if (!mem_pool) return fail(IPMCMC_ECUDA, "cannot create the arena memory pool");
+    CUDA_TRY(cudaMallocFromPoolAsync((void **)&arena, n_dbl * sizeof(double) + (B * CNT_N + n_sched) * sizeof(long long) + pool_bytes,
+                                     mem_pool, st));
     double *u = arena, *phi = u + B * d, *cnt = phi + B, *mean = cnt + B, *m2 = mean + B * d, *pooled = m2 + B * d;
     double *mstate = pooled + (2 * d + 7), *trace = mstate + B * nvar;
     long long *counters = (long long *)(trace + n_trace), *sched = counters + B * CNT_N;

@@ -17,5 +17,4 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:burg
 timeout 300 $L > gpurun_out/r2b_plain_l.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:lorenz_chain_queue -s 3 -c 1 -o gpurun_out/r2b_lorenz_final $L > gpurun_out/r2b_lorenz_ncu.log 2>&1
 bash tools/ncu_export.sh > /dev/null 2>&1
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_target.py > gpurun_out/r2b_memcheck.log 2>&1; echo memcheck rc=$? >> gpurun_out/r2b_memcheck.log; tail -4 gpurun_out/r2b_memcheck.log
 ls gpurun_out
