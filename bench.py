@@ -348,6 +348,11 @@ def main():
         sampler_clk.start()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K + 1)]
         launches0 = chains.launches
+        if world > 1:
+            # align the ranks ON THE DEVICE: the streams wait in a one-element all-reduce until every rank has reached
+            # this point, so the host-side skew of eight Python processes (tens of milliseconds: thread start, NVML)
+            # does not show up as waiting time in the final collective of the ranks that started early
+            dist.all_reduce(torch.zeros(1, dtype=F64, device=dev))
         t_wall0 = time.perf_counter()
         for k in range(K):
             flush.zero_()                                   # evict L2 between timed launches (untimed)
