@@ -123,3 +123,46 @@ def test_lorenz_bench_config_statistics_vs_cpu_chains(G):
     _compare(dev, cpu, "lorenz RW T=20")
     # same integrator work: RK45 attempts per solve within 2 % (controller parity at the statistical level)
     assert abs(attempts_dev - attempts_cpu) < 0.02 * attempts_cpu, (attempts_dev, attempts_cpu)
+
+
+@pytest.mark.parametrize("kind", ["pcn", "rw"])
+def test_flat_likelihood_exact_stationary_law(G, kind):
+    """Sampler-correctness control with a KNOWN answer ('exact check'): with a noise covariance of
+    1e12 the misfit is flat to 1e-10, so the stationary law of the chain is the Gaussian its proposer / accepter
+    pair targets, N(0, C) -- for pCN because every proposal is accepted and v = sqrt(1-beta^2) u + beta w is
+    an AR(1) process with that law (proposer.py:78-81), for RW because exp(I(u) - I(v)), I(w) = 1/2 |L w|^2
+    (accepter.py:99-106), is the Metropolis ratio of N(0, (L^T L)^-1) = N(0, C) when C = I.  The end states of
+    4096 independent chains are 4096 independent draws: mean and variance must agree with 0 and 1 within
+    4 standard errors (sd/sqrt(n) and sqrt(2/(n-1))), the pooled device moments with the recorded states."""
+    import ip_mcmc_b200 as M
+    n_chains, n_steps = 4096, 300
+    # the step cap is lifted: the blow-up solves of the reference's interior-only CFL (DESIGN 7; 0.2 % of the steps under
+    # this wide prior) finish with a finite, equally flat misfit instead of being rejected as capped
+    f = M.BurgersFVM(N=32, numerics="fused", max_fv_steps=10 ** 7)
+    prior = M.GaussianDistribution(G.PRIOR_MEAN, np.identity(3))
+    pot = M.EvolutionPotential(f, f.at_parameters(G.TRUTH), M.GaussianDistribution(np.zeros(5), 1e12 * np.identity(5)))
+    if kind == "pcn":
+        s = M.MCMCSampler(M.ConstSteppCNProposer(0.5, prior), M.CountedAccepter(M.pCNAccepter(pot)), np.random.default_rng(5))
+    else:
+        s = M.MCMCSampler(M.ConstStepStandardRWProposer(0.5, prior), M.CountedAccepter(M.StandardRWAccepter(pot, prior)),
+                          np.random.default_rng(6))
+    states = s.run(np.zeros(3), n_steps, 0, 1, n_chains=n_chains)
+    c = s.last_run["counters"]
+    assert c["nonfinite"] < 1e-4 * c["calls"], c
+    end = states[:, -1]
+    z_mean = end.mean(0) * np.sqrt(n_chains) / end.std(0, ddof=1)
+    z_var = (end.var(0, ddof=1) - 1.0) / np.sqrt(2.0 / (n_chains - 1))
+    msg = "%s: acceptance %.4f, end-state mean z %s, variance z %s" % (kind, c["accepts"] / c["calls"], np.round(z_mean, 2), np.round(z_var, 2))
+    print(msg)
+    assert np.all(np.abs(z_mean) < Z_MAX) and np.all(np.abs(z_var) < Z_MAX), msg
+    if kind == "pcn":
+        assert c["accepts"] >= 0.999 * (c["calls"] - c["nonfinite"]), msg
+        # AR(1) with rho = sqrt(1 - beta^2): lag-1 autocorrelation of the recorded chains
+        x = states[:, 100:]
+        rho = np.mean(x[:, 1:] * x[:, :-1]) / np.mean(x * x)
+        assert abs(rho - np.sqrt(0.75)) < 5e-3, rho
+    else:
+        assert 0.2 < c["accepts"] / c["calls"] < 0.6, msg   # RW Metropolis on N(0, I_3), proposal sd 1
+    flat = states.reshape(-1, 3)
+    np.testing.assert_allclose(s.last_run["pooled_mean"], flat.mean(0), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(s.last_run["pooled_var"], flat.var(0, ddof=1), rtol=1e-9)
