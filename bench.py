@@ -134,8 +134,9 @@ def cpu_baselines(wl, cores):
 
 
 def cpu_steps_for(wl):
-    # bounded sample: ~10 s of work per process at N = 256 (~70 chain-steps/s/core), ~15 s at N = 1024, ~12 s Lorenz
-    return {"burgers": 600 if wl.get("N", 0) <= 256 else 12, "lorenz": 2}[wl["model"]]
+    # bounded sample per process (16 of them on the box's 16 cores): ~13 s at N = 256 (~70 chain-steps/s/core),
+    # ~3 s at N = 1024 (~13 /s/core), ~5 s Lorenz (~1.2 /s/core)
+    return {"burgers": 900 if wl.get("N", 0) <= 256 else 40, "lorenz": 6}[wl["model"]]
 
 
 def posterior_start(wl):
@@ -152,7 +153,7 @@ def run_reference(args, wl, name, out_fd):
         return
     cores = os.cpu_count() or 1
     # bounded sample per bench step, shrunk for long runs so that the whole arm stays within a few minutes
-    n = max(1, min(cpu_steps_for(wl), cpu_steps_for(wl) * 12 // max(args.steps, 1)))
+    n = max(1, min(cpu_steps_for(wl), cpu_steps_for(wl) * 7 // max(args.steps, 1)))      # <= ~90 s of chains in total
     u_start = posterior_start(wl)
     for _ in range(args.warmup if args.warmup < 2 else 1):      # process start-up / import warm-up
         cpu_sample(wl, 1, cores, u_start)
