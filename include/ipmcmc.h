@@ -278,7 +278,7 @@ typedef struct ipmcmc_host_io {
     int64_t *counters_host;    /* OUT [n_chains, 6], or NULL                                        */
     double *pooled_host;       /* OUT [2d + 7] pooled moments + counters, or NULL                   */
     int32_t scheduler;         /* 0: dynamic step scheduler where available (default), 1: static    */
-    int32_t sched_chunk;       /* Metropolis steps per work item (<= 0: min(4, max(1, n_steps/64))) */
+    int32_t sched_chunk;       /* Metropolis steps per work item (<= 0: Burgers min(4, max(1, n_steps/64)), Lorenz 1) */
 } ipmcmc_host_io;
 
 int ipmcmc_sample_host(ipmcmc_problem *p, const ipmcmc_sampler_desc *s, int64_t n_chains,

@@ -745,7 +745,8 @@ extern "C" int ipmcmc_sample_host(ipmcmc_problem *p, const ipmcmc_sampler_desc *
     if (queue) {   // the dynamic step scheduler, like ChainBatch (the fast path)
         cb.sched_dev = (int64_t *)sched;
         cb.sched_len = (int64_t)n_sched;
-        const int64_t auto_chunk = n_steps / 64 < 1 ? 1 : (n_steps / 64 > 4 ? 4 : n_steps / 64);
+        // Metropolis steps per work item (engine.py, ChainBatch.run: same rule): a Lorenz item is already ~1.7 ms of solves
+        const int64_t auto_chunk = p->model == IPMCMC_MODEL_LORENZ ? 1 : (n_steps / 64 < 1 ? 1 : (n_steps / 64 > 4 ? 4 : n_steps / 64));
         cb.sched_chunk = io->sched_chunk > 0 ? io->sched_chunk : (int32_t)auto_chunk;
     }
     rc = ipmcmc_run(p, s, &cb, n_chains, n_steps, stream);

@@ -230,7 +230,7 @@ class ChainBatch:
         self.placement = None
         self._work_prev = None
         self.sched = None          # scratch of the dynamic step scheduler (Burgers N <= 1024, Lorenz)
-        self.sched_chunk = 0       # Metropolis steps per work item; 0 = min(4, max(1, n_steps // 64)) per launch
+        self.sched_chunk = 0       # Metropolis steps per work item; 0 = automatic (Burgers: min(4, max(1, n_steps // 64)); Lorenz: 1)
         if problem.kind == _lib.MODEL_LORENZ:
             if scheduler == "dynamic":
                 self.sched = torch.empty((3 * self.n + 2,), dtype=torch.int64, device=dev)
@@ -267,9 +267,12 @@ class ChainBatch:
         if self.sched is not None:
             b.sched_dev = _ptr(self.sched)
             b.sched_len = self.sched.numel()
-            # a work item costs ~4 us of queue traffic and state reloads: long launches use longer
-            # items (measured on B200, 1024 x 256 cells: +1 % at 200 steps per launch; 50 steps: none)
-            b.sched_chunk = self.sched_chunk or min(4, max(1, int(n_steps) // 64))
+            # a work item costs ~4 us of queue traffic and state reloads: long Burgers launches use longer
+            # items (measured on B200, 1024 x 256 cells: +1 % at 200 steps per launch; 50 steps: none).  A Lorenz
+            # item is two RK45 solves of a warp's chain group (~1.7 ms): one step per item balances best
+            # (4096 chains, 128 steps per launch: 1.87 M chain-steps/s against 1.83 M with two steps per item)
+            auto = 1 if self.problem.kind == _lib.MODEL_LORENZ else min(4, max(1, int(n_steps) // 64))
+            b.sched_chunk = self.sched_chunk or auto
         pl = self.placement
         if pl is not None:
             b.warps_per_cta = pl.W
